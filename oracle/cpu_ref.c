@@ -1,0 +1,527 @@
+/* CPU oracle for the BLS12-381 hot path -- TEST INFRASTRUCTURE ONLY.
+ *
+ * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference
+ * legs may load this library; the product (crypto_b200/, libdockgpu.so) never does.
+ *
+ * What it restates: the arkworks 0.4 algorithms the reference calls on its hot path
+ * (SURVEY.md section 8a / Appendix B).  The arithmetic is in the third-party crates
+ * ark-ec ^0.4.1, ark-ff ^0.4.1, ark-bls12-381 ^0.4.0 (/root/reference/Cargo.toml:32-46),
+ * which are NOT vendored and whose exact patch version is unpinned (no Cargo.lock), so
+ * the published algorithms are restated:
+ *   ref_msm_g1/g2          VariableBaseMSM::msm_bigint (msm_bigint_wnaf): window rule
+ *                          c = ln_without_floats(n)+2, signed digits, rayon-over-windows
+ *                          -> OpenMP over windows.  Call sites: legogroth16/src/prover.rs:286,
+ *                          299,363,592; bbs_plus/src/setup.rs:145; schnorr_pok/src/
+ *                          pok_generalized_pedersen.rs:97; vb_accumulator/src/witness.rs:415
+ *   ref_fixed_base_*       FixedBase::get_window_table / msm behind utils/src/msm.rs:18-62
+ *   ref_batch_mul_g1       AffineRepr::mul_bigint per element (vb_accumulator/src/witness.rs:190)
+ *   ref_normalize_batch_g1 CurveGroup::normalize_batch (vb_accumulator/src/witness.rs:193)
+ *   ref_multi_miller_loop, ref_final_exp
+ *                          ark_ec::models::bls12 (G2Prepared line coefficients, M-twist ell,
+ *                          conjugate for x<0; final exponentiation chain of eprint 2020/875)
+ *                          reached from utils/src/randomized_pairing_check.rs:204-214,
+ *                          bbs_plus/src/proof.rs:494, legogroth16/src/verifier.rs:69-80
+ *
+ * PARITY STATUS: "parity unpinned" by the reference (it holds no golden vectors for this
+ * path).  Pinned instead against oracle/bls12_381.py (big-int, two independent pairing
+ * derivations) by tests/test_oracle.py and the vectors in tests/golden/.
+ *
+ * 6 x 64-bit Montgomery limbs (R = 2^384), unsigned __int128 products: the same
+ * representation as ark-ff's MontBackend, so Montgomery bytes cross unchanged.
+ */
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+#include "bls_consts.h"
+
+typedef unsigned __int128 u128;
+typedef struct { uint64_t l[6]; } fp_t;
+typedef struct { fp_t c0, c1; } fp2_t;
+typedef struct { fp2_t c0, c1, c2; } fp6_t;
+typedef struct { fp6_t c0, c1; } fp12_t;
+
+/* ------------------------------------------------------------------ Fp --- */
+static inline void fp_set_zero(fp_t *r) { memset(r, 0, sizeof *r); }
+static inline void fp_set_one(fp_t *r) { memcpy(r->l, FPC_R_ONE, 48); }
+static inline int fp_is_zero(const fp_t *a) { uint64_t t = 0; for (int i = 0; i < 6; i++) t |= a->l[i]; return t == 0; }
+static inline int fp_eq(const fp_t *a, const fp_t *b) { return memcmp(a, b, 48) == 0; }
+
+static inline int fp_geq_p(const uint64_t a[6]) {
+    for (int i = 5; i >= 0; i--) { if (a[i] > FPC_P[i]) return 1; if (a[i] < FPC_P[i]) return 0; }
+    return 1;
+}
+static inline void fp_sub_p(uint64_t a[6]) {
+    u128 br = 0;
+    for (int i = 0; i < 6; i++) { u128 t = (u128)a[i] - FPC_P[i] - br; a[i] = (uint64_t)t; br = (t >> 64) & 1; }
+}
+static inline void fp_add(fp_t *r, const fp_t *a, const fp_t *b) {
+    u128 c = 0; uint64_t t[6];
+    for (int i = 0; i < 6; i++) { c += (u128)a->l[i] + b->l[i]; t[i] = (uint64_t)c; c >>= 64; }
+    if (fp_geq_p(t)) fp_sub_p(t);
+    memcpy(r->l, t, 48);
+}
+static inline void fp_sub(fp_t *r, const fp_t *a, const fp_t *b) {
+    u128 br = 0; uint64_t t[6];
+    for (int i = 0; i < 6; i++) { u128 d = (u128)a->l[i] - b->l[i] - br; t[i] = (uint64_t)d; br = (d >> 64) & 1; }
+    if (br) { u128 c = 0; for (int i = 0; i < 6; i++) { c += (u128)t[i] + FPC_P[i]; t[i] = (uint64_t)c; c >>= 64; } }
+    memcpy(r->l, t, 48);
+}
+static inline void fp_neg(fp_t *r, const fp_t *a) { fp_t z; fp_set_zero(&z); if (fp_is_zero(a)) { *r = z; return; } fp_sub(r, &z, a); }
+
+/* CIOS Montgomery multiplication */
+static inline void fp_mul(fp_t *r, const fp_t *a, const fp_t *b) {
+    uint64_t t[8] = {0};
+    for (int i = 0; i < 6; i++) {
+        u128 c = 0;
+        for (int j = 0; j < 6; j++) { c += (u128)a->l[j] * b->l[i] + t[j]; t[j] = (uint64_t)c; c >>= 64; }
+        c += t[6]; t[6] = (uint64_t)c; t[7] = (uint64_t)(c >> 64);
+        uint64_t m = t[0] * FP_INV64;
+        c = (u128)m * FPC_P[0] + t[0]; c >>= 64;
+        for (int j = 1; j < 6; j++) { c += (u128)m * FPC_P[j] + t[j]; t[j - 1] = (uint64_t)c; c >>= 64; }
+        c += t[6]; t[5] = (uint64_t)c; t[6] = t[7] + (uint64_t)(c >> 64);
+    }
+    if (t[6] || fp_geq_p(t)) fp_sub_p(t);
+    memcpy(r->l, t, 48);
+}
+static inline void fp_sqr(fp_t *r, const fp_t *a) { fp_mul(r, a, a); }
+
+static void fp_pow(fp_t *r, const fp_t *a, const uint64_t *e, int nlimbs) {
+    fp_t acc; fp_set_one(&acc);
+    for (int i = nlimbs * 64 - 1; i >= 0; i--) {
+        fp_sqr(&acc, &acc);
+        if ((e[i >> 6] >> (i & 63)) & 1) fp_mul(&acc, &acc, a);
+    }
+    *r = acc;
+}
+static void fp_inv(fp_t *r, const fp_t *a) {           /* a^(p-2); inv(0) = 0 */
+    uint64_t e[6]; memcpy(e, FPC_P, 48); e[0] -= 2;
+    fp_pow(r, a, e, 6);
+}
+
+/* ------------------------------------------------------------------ Fp2 -- */
+static inline void fp2_set_zero(fp2_t *r) { fp_set_zero(&r->c0); fp_set_zero(&r->c1); }
+static inline void fp2_set_one(fp2_t *r) { fp_set_one(&r->c0); fp_set_zero(&r->c1); }
+static inline int fp2_is_zero(const fp2_t *a) { return fp_is_zero(&a->c0) && fp_is_zero(&a->c1); }
+static inline int fp2_eq(const fp2_t *a, const fp2_t *b) { return fp_eq(&a->c0, &b->c0) && fp_eq(&a->c1, &b->c1); }
+static inline void fp2_add(fp2_t *r, const fp2_t *a, const fp2_t *b) { fp_add(&r->c0, &a->c0, &b->c0); fp_add(&r->c1, &a->c1, &b->c1); }
+static inline void fp2_sub(fp2_t *r, const fp2_t *a, const fp2_t *b) { fp_sub(&r->c0, &a->c0, &b->c0); fp_sub(&r->c1, &a->c1, &b->c1); }
+static inline void fp2_neg(fp2_t *r, const fp2_t *a) { fp_neg(&r->c0, &a->c0); fp_neg(&r->c1, &a->c1); }
+static inline void fp2_conj(fp2_t *r, const fp2_t *a) { r->c0 = a->c0; fp_neg(&r->c1, &a->c1); }
+static inline void fp2_mul(fp2_t *r, const fp2_t *a, const fp2_t *b) {
+    fp_t t0, t1, s0, s1, m;
+    fp_mul(&t0, &a->c0, &b->c0); fp_mul(&t1, &a->c1, &b->c1);
+    fp_add(&s0, &a->c0, &a->c1); fp_add(&s1, &b->c0, &b->c1);
+    fp_mul(&m, &s0, &s1);
+    fp_sub(&r->c0, &t0, &t1);
+    fp_sub(&m, &m, &t0); fp_sub(&r->c1, &m, &t1);
+}
+static inline void fp2_sqr(fp2_t *r, const fp2_t *a) {
+    fp_t s, d, m;
+    fp_add(&s, &a->c0, &a->c1); fp_sub(&d, &a->c0, &a->c1);
+    fp_mul(&m, &a->c0, &a->c1);
+    fp_mul(&r->c0, &s, &d); fp_add(&r->c1, &m, &m);
+}
+static inline void fp2_mul_fp(fp2_t *r, const fp2_t *a, const fp_t *k) { fp_mul(&r->c0, &a->c0, k); fp_mul(&r->c1, &a->c1, k); }
+static inline void fp2_mul_xi(fp2_t *r, const fp2_t *a) {       /* times (1+u) */
+    fp_t t0, t1; fp_sub(&t0, &a->c0, &a->c1); fp_add(&t1, &a->c0, &a->c1); r->c0 = t0; r->c1 = t1;
+}
+static void fp2_inv(fp2_t *r, const fp2_t *a) {
+    fp_t n, t; fp_sqr(&n, &a->c0); fp_sqr(&t, &a->c1); fp_add(&n, &n, &t); fp_inv(&n, &n);
+    fp_mul(&r->c0, &a->c0, &n); fp_mul(&t, &a->c1, &n); fp_neg(&r->c1, &t);
+}
+
+/* ------------------------------------------------------------------ Fp6 -- */
+static void fp6_add(fp6_t *r, const fp6_t *a, const fp6_t *b) { fp2_add(&r->c0, &a->c0, &b->c0); fp2_add(&r->c1, &a->c1, &b->c1); fp2_add(&r->c2, &a->c2, &b->c2); }
+static void fp6_sub(fp6_t *r, const fp6_t *a, const fp6_t *b) { fp2_sub(&r->c0, &a->c0, &b->c0); fp2_sub(&r->c1, &a->c1, &b->c1); fp2_sub(&r->c2, &a->c2, &b->c2); }
+static void fp6_neg(fp6_t *r, const fp6_t *a) { fp2_neg(&r->c0, &a->c0); fp2_neg(&r->c1, &a->c1); fp2_neg(&r->c2, &a->c2); }
+static void fp6_mul(fp6_t *r, const fp6_t *a, const fp6_t *b) {
+    fp2_t t0, t1, t2, x, y, c0, c1, c2;
+    fp2_mul(&t0, &a->c0, &b->c0); fp2_mul(&t1, &a->c1, &b->c1); fp2_mul(&t2, &a->c2, &b->c2);
+    fp2_add(&x, &a->c1, &a->c2); fp2_add(&y, &b->c1, &b->c2); fp2_mul(&c0, &x, &y);
+    fp2_sub(&c0, &c0, &t1); fp2_sub(&c0, &c0, &t2); fp2_mul_xi(&c0, &c0); fp2_add(&c0, &c0, &t0);
+    fp2_add(&x, &a->c0, &a->c1); fp2_add(&y, &b->c0, &b->c1); fp2_mul(&c1, &x, &y);
+    fp2_sub(&c1, &c1, &t0); fp2_sub(&c1, &c1, &t1); fp2_mul_xi(&x, &t2); fp2_add(&c1, &c1, &x);
+    fp2_add(&x, &a->c0, &a->c2); fp2_add(&y, &b->c0, &b->c2); fp2_mul(&c2, &x, &y);
+    fp2_sub(&c2, &c2, &t0); fp2_sub(&c2, &c2, &t2); fp2_add(&c2, &c2, &t1);
+    r->c0 = c0; r->c1 = c1; r->c2 = c2;
+}
+static void fp6_mul_v(fp6_t *r, const fp6_t *a) { fp2_t t; fp2_mul_xi(&t, &a->c2); r->c2 = a->c1; r->c1 = a->c0; r->c0 = t; }
+static void fp6_inv(fp6_t *r, const fp6_t *a) {
+    fp2_t t0, t1, t2, x, d;
+    fp2_sqr(&t0, &a->c0); fp2_mul(&x, &a->c1, &a->c2); fp2_mul_xi(&x, &x); fp2_sub(&t0, &t0, &x);
+    fp2_sqr(&t1, &a->c2); fp2_mul_xi(&t1, &t1); fp2_mul(&x, &a->c0, &a->c1); fp2_sub(&t1, &t1, &x);
+    fp2_sqr(&t2, &a->c1); fp2_mul(&x, &a->c0, &a->c2); fp2_sub(&t2, &t2, &x);
+    fp2_mul(&d, &a->c2, &t1); fp2_mul(&x, &a->c1, &t2); fp2_add(&d, &d, &x); fp2_mul_xi(&d, &d);
+    fp2_mul(&x, &a->c0, &t0); fp2_add(&d, &d, &x);
+    fp2_inv(&d, &d);
+    fp2_mul(&r->c0, &t0, &d); fp2_mul(&r->c1, &t1, &d); fp2_mul(&r->c2, &t2, &d);
+}
+
+/* ------------------------------------------------------------------ Fp12 - */
+static void fp12_set_one(fp12_t *r) { memset(r, 0, sizeof *r); fp_set_one(&r->c0.c0.c0); }
+static int fp12_is_zero(const fp12_t *a) { const uint64_t *w = (const uint64_t *)a; uint64_t t = 0; for (int i = 0; i < 72; i++) t |= w[i]; return t == 0; }
+static void fp12_mul(fp12_t *r, const fp12_t *a, const fp12_t *b) {
+    fp6_t t0, t1, x, y, c1;
+    fp6_mul(&t0, &a->c0, &b->c0); fp6_mul(&t1, &a->c1, &b->c1);
+    fp6_add(&x, &a->c0, &a->c1); fp6_add(&y, &b->c0, &b->c1); fp6_mul(&c1, &x, &y);
+    fp6_sub(&c1, &c1, &t0); fp6_sub(&c1, &c1, &t1);
+    fp6_mul_v(&x, &t1); fp6_add(&r->c0, &t0, &x);
+    r->c1 = c1;
+}
+static void fp12_sqr(fp12_t *r, const fp12_t *a) { fp12_mul(r, a, a); }
+static void fp12_conj(fp12_t *r, const fp12_t *a) { r->c0 = a->c0; fp6_neg(&r->c1, &a->c1); }
+static void fp12_inv(fp12_t *r, const fp12_t *a) {
+    fp6_t d, t;
+    fp6_mul(&d, &a->c0, &a->c0); fp6_mul(&t, &a->c1, &a->c1); fp6_mul_v(&t, &t); fp6_sub(&d, &d, &t);
+    fp6_inv(&d, &d);
+    fp6_mul(&r->c0, &a->c0, &d); fp6_mul(&t, &a->c1, &d); fp6_neg(&r->c1, &t);
+}
+static void fp12_frobenius(fp12_t *r, const fp12_t *a, int k) {
+    const uint64_t (*g)[2][6] = k == 1 ? FPC_FROB1 : k == 2 ? FPC_FROB2 : FPC_FROB3;
+    fp2_t *dst[6] = {&r->c0.c0, &r->c1.c0, &r->c0.c1, &r->c1.c1, &r->c0.c2, &r->c1.c2};
+    const fp2_t *src[6] = {&a->c0.c0, &a->c1.c0, &a->c0.c1, &a->c1.c1, &a->c0.c2, &a->c1.c2};
+    for (int i = 0; i < 6; i++) {            /* basis element w^i picks up xi^(i(p^k-1)/6) */
+        fp2_t t = *src[i], c;
+        if (k & 1) fp2_conj(&t, &t);
+        memcpy(c.c0.l, g[i][0], 48); memcpy(c.c1.l, g[i][1], 48);
+        fp2_mul(dst[i], &t, &c);
+    }
+}
+/* f *= (c0 + c1 v + c4 v w) -- ark Fp12::mul_by_014 */
+static void fp12_mul_by_014(fp12_t *f, const fp2_t *c0, const fp2_t *c1, const fp2_t *c4) {
+    fp12_t s; memset(&s, 0, sizeof s);
+    s.c0.c0 = *c0; s.c0.c1 = *c1; s.c1.c1 = *c4;
+    fp12_mul(f, f, &s);
+}
+#define BLS_X_ABS 0xd201000000010000ULL
+static void fp12_exp_by_x(fp12_t *r, const fp12_t *a) {   /* a^|x| then conjugate (x<0) */
+    fp12_t acc; fp12_set_one(&acc);
+    for (int i = 63; i >= 0; i--) {
+        fp12_sqr(&acc, &acc);
+        if ((BLS_X_ABS >> i) & 1) fp12_mul(&acc, &acc, a);
+    }
+    fp12_conj(r, &acc);
+}
+
+/* ------------------------------------------------------ scalars / windows -- */
+static int ceil_log2(size_t n) { int l = 0; while (((size_t)1 << l) < n) l++; return l; }
+static int ln_without_floats(size_t n) { return ceil_log2(n) * 69 / 100; }
+static int msm_window_size(size_t n) { return n < 32 ? 3 : ln_without_floats(n) + 2; }
+static int fixed_base_window_size(size_t n) { return n < 32 ? 3 : ln_without_floats(n); }
+
+/* ark make_digits: signed radix-2^c digits of a 256-bit canonical integer */
+static void make_digits(int32_t *out, const uint64_t s[4], int c, int nd) {
+    int64_t radix = (int64_t)1 << c, half = radix >> 1, carry = 0;
+    for (int i = 0; i < nd; i++) {
+        int bit = i * c;
+        uint64_t v = 0;
+        if (bit < 256) {
+            int w = bit >> 6, off = bit & 63;
+            v = s[w] >> off;
+            if (off + c > 64 && w + 1 < 4) v |= s[w + 1] << (64 - off);
+            v &= (uint64_t)radix - 1;
+        }
+        int64_t d = (int64_t)v + carry;
+        carry = (d + half) >> c;
+        d -= carry << c;
+        if (i == nd - 1) d += carry << c;
+        out[i] = (int32_t)d;
+    }
+}
+
+/* -------------------------------------------------------- G1 / G2 --------- */
+#define FE fp_t
+#define FN(x) fp_##x
+#define PN(x) g1_##x
+#include "ec_tmpl.h"
+#undef FE
+#undef FN
+#undef PN
+#define FE fp2_t
+#define FN(x) fp2_##x
+#define PN(x) g2_##x
+#include "ec_tmpl.h"
+#undef FE
+#undef FN
+#undef PN
+
+/* packed wire records of the C ABI: identity = all-zero coordinates */
+static void g1_load(g1_aff *p, const uint8_t *b) {
+    memcpy(&p->x, b, 48); memcpy(&p->y, b + 48, 48);
+    p->inf = fp_is_zero(&p->x) && fp_is_zero(&p->y);
+}
+static void g1_store(uint8_t *b, const g1_aff *p) {
+    if (p->inf) { memset(b, 0, 96); return; }
+    memcpy(b, &p->x, 48); memcpy(b + 48, &p->y, 48);
+}
+static void g2_load(g2_aff *p, const uint8_t *b) {
+    memcpy(&p->x, b, 96); memcpy(&p->y, b + 96, 96);
+    p->inf = fp2_is_zero(&p->x) && fp2_is_zero(&p->y);
+}
+static void g2_store(uint8_t *b, const g2_aff *p) {
+    if (p->inf) { memset(b, 0, 192); return; }
+    memcpy(b, &p->x, 96); memcpy(b + 96, &p->y, 96);
+}
+
+/* -------------------------------------------------------- pairing --------- */
+typedef struct { fp2_t c0, c1, c2; } ell_coeff;
+#define N_ELL 68
+
+static void g2_prepare(ell_coeff *co, const g2_aff *q) {
+    fp2_t rx = q->x, ry = q->y, rz; fp2_set_one(&rz);
+    fp_t two_inv; memcpy(two_inv.l, FPC_TWO_INV, 48);
+    fp2_t B; memcpy(B.c0.l, FPC_B_G1, 48); memcpy(B.c1.l, FPC_B_G1, 48);   /* 4 + 4u */
+    int n = 0;
+    for (int i = 62; i >= 0; i--) {
+        {   /* doubling step */
+            fp2_t a, b, c, e, f, g, h, ii, j, e2, t;
+            fp2_mul(&a, &rx, &ry); fp2_mul_fp(&a, &a, &two_inv);
+            fp2_sqr(&b, &ry); fp2_sqr(&c, &rz);
+            fp2_add(&t, &c, &c); fp2_add(&t, &t, &c); fp2_mul(&e, &B, &t);
+            fp2_add(&f, &e, &e); fp2_add(&f, &f, &e);
+            fp2_add(&g, &b, &f); fp2_mul_fp(&g, &g, &two_inv);
+            fp2_add(&h, &ry, &rz); fp2_sqr(&h, &h); fp2_add(&t, &b, &c); fp2_sub(&h, &h, &t);
+            fp2_sub(&ii, &e, &b);
+            fp2_sqr(&j, &rx);
+            fp2_sqr(&e2, &e);
+            fp2_sub(&t, &b, &f); fp2_mul(&rx, &a, &t);
+            fp2_sqr(&ry, &g); fp2_add(&t, &e2, &e2); fp2_add(&t, &t, &e2); fp2_sub(&ry, &ry, &t);
+            fp2_mul(&rz, &b, &h);
+            co[n].c0 = ii; fp2_add(&t, &j, &j); fp2_add(&co[n].c1, &t, &j); fp2_neg(&co[n].c2, &h);
+            n++;
+        }
+        if ((BLS_X_ABS >> i) & 1) {   /* addition step */
+            fp2_t theta, lam, c, d, e, f, g, h, j, t;
+            fp2_mul(&t, &q->y, &rz); fp2_sub(&theta, &ry, &t);
+            fp2_mul(&t, &q->x, &rz); fp2_sub(&lam, &rx, &t);
+            fp2_sqr(&c, &theta); fp2_sqr(&d, &lam);
+            fp2_mul(&e, &lam, &d); fp2_mul(&f, &rz, &c); fp2_mul(&g, &rx, &d);
+            fp2_add(&h, &e, &f); fp2_sub(&h, &h, &g); fp2_sub(&h, &h, &g);
+            fp2_mul(&rx, &lam, &h);
+            fp2_sub(&t, &g, &h); fp2_mul(&t, &theta, &t); fp2_mul(&ry, &e, &ry); fp2_sub(&ry, &t, &ry);
+            fp2_mul(&rz, &rz, &e);
+            fp2_mul(&j, &theta, &q->x); fp2_mul(&t, &lam, &q->y); fp2_sub(&j, &j, &t);
+            co[n].c0 = j; fp2_neg(&co[n].c1, &theta); co[n].c2 = lam;
+            n++;
+        }
+    }
+}
+
+static void ell(fp12_t *f, const ell_coeff *co, const g1_aff *p) {
+    fp2_t c1, c2;
+    fp2_mul_fp(&c2, &co->c2, &p->y);
+    fp2_mul_fp(&c1, &co->c1, &p->x);
+    fp12_mul_by_014(f, &co->c0, &c1, &c2);
+}
+
+/* ================================================================= exports == */
+#define EXPORT __attribute__((visibility("default")))
+
+EXPORT int ref_msm_window_size(size_t n) { return msm_window_size(n); }
+EXPORT int ref_fixed_base_window_size(size_t n) { return fixed_base_window_size(n); }
+
+/* out: Jacobian 144 B (ark Projective x,y,z) */
+EXPORT void ref_msm_g1(const uint8_t *bases, const uint8_t *scalars, size_t n, uint8_t *out_jac) {
+    g1_aff *b = (g1_aff *)malloc(sizeof(g1_aff) * (n ? n : 1));
+#pragma omp parallel for
+    for (size_t i = 0; i < n; i++) g1_load(&b[i], bases + 96 * i);
+    g1_jac r; g1_msm_bigint(&r, b, (const uint64_t *)scalars, n);
+    memcpy(out_jac, &r, 144);
+    free(b);
+}
+EXPORT void ref_msm_g2(const uint8_t *bases, const uint8_t *scalars, size_t n, uint8_t *out_jac) {
+    g2_aff *b = (g2_aff *)malloc(sizeof(g2_aff) * (n ? n : 1));
+#pragma omp parallel for
+    for (size_t i = 0; i < n; i++) g2_load(&b[i], bases + 192 * i);
+    g2_jac r; g2_msm_bigint(&r, b, (const uint64_t *)scalars, n);
+    memcpy(out_jac, &r, 288);
+    free(b);
+}
+
+EXPORT void ref_normalize_batch_g1(const uint8_t *jac, size_t n, uint8_t *out_aff) {
+    g1_aff *a = (g1_aff *)malloc(sizeof(g1_aff) * (n ? n : 1));
+    g1_normalize_batch(a, (const g1_jac *)jac, n);
+    for (size_t i = 0; i < n; i++) g1_store(out_aff + 96 * i, &a[i]);
+    free(a);
+}
+EXPORT void ref_normalize_batch_g2(const uint8_t *jac, size_t n, uint8_t *out_aff) {
+    g2_aff *a = (g2_aff *)malloc(sizeof(g2_aff) * (n ? n : 1));
+    g2_normalize_batch(a, (const g2_jac *)jac, n);
+    for (size_t i = 0; i < n; i++) g2_store(out_aff + 192 * i, &a[i]);
+    free(a);
+}
+
+/* [s_i] P_i, out Jacobian m x 144 B */
+EXPORT void ref_batch_mul_g1(const uint8_t *points, const uint8_t *scalars, size_t m, uint8_t *out_jac) {
+#pragma omp parallel for schedule(dynamic, 16)
+    for (size_t i = 0; i < m; i++) {
+        g1_aff p; g1_load(&p, points + 96 * i);
+        g1_jac r; g1_mul_bigint(&r, &p, (const uint64_t *)(scalars + 32 * i));
+        memcpy(out_jac + 144 * i, &r, 144);
+    }
+}
+EXPORT void ref_batch_mul_g2(const uint8_t *points, const uint8_t *scalars, size_t m, uint8_t *out_jac) {
+#pragma omp parallel for schedule(dynamic, 16)
+    for (size_t i = 0; i < m; i++) {
+        g2_aff p; g2_load(&p, points + 192 * i);
+        g2_jac r; g2_mul_bigint(&r, &p, (const uint64_t *)(scalars + 32 * i));
+        memcpy(out_jac + 288 * i, &r, 288);
+    }
+}
+
+/* WindowTable::new(hint_n, g) + multiply_many(scalars): out Jacobian m x 144 B.
+ * Also returns the table geometry (window, num_windows) like utils/src/msm.rs:8-13. */
+EXPORT void ref_fixed_base_mul_many_g1(const uint8_t *point, size_t hint_n, const uint8_t *scalars, size_t m,
+                                       uint8_t *out_jac, int *window_out, int *num_windows_out) {
+    g1_aff g; g1_load(&g, point);
+    int window = fixed_base_window_size(hint_n), outerc;
+    g1_aff *table = g1_fixed_base_table(&g, window, &outerc);
+#pragma omp parallel for schedule(dynamic, 64)
+    for (size_t i = 0; i < m; i++) {
+        g1_jac r; g1_windowed_mul(&r, table, window, outerc, (const uint64_t *)(scalars + 32 * i));
+        memcpy(out_jac + 144 * i, &r, 144);
+    }
+    if (window_out) *window_out = window;
+    if (num_windows_out) *num_windows_out = outerc;
+    free(table);
+}
+EXPORT void ref_fixed_base_mul_many_g2(const uint8_t *point, size_t hint_n, const uint8_t *scalars, size_t m,
+                                       uint8_t *out_jac, int *window_out, int *num_windows_out) {
+    g2_aff g; g2_load(&g, point);
+    int window = fixed_base_window_size(hint_n), outerc;
+    g2_aff *table = g2_fixed_base_table(&g, window, &outerc);
+#pragma omp parallel for schedule(dynamic, 64)
+    for (size_t i = 0; i < m; i++) {
+        g2_jac r; g2_windowed_mul(&r, table, window, outerc, (const uint64_t *)(scalars + 32 * i));
+        memcpy(out_jac + 288 * i, &r, 288);
+    }
+    if (window_out) *window_out = window;
+    if (num_windows_out) *num_windows_out = outerc;
+    free(table);
+}
+/* Row-major window table itself (num_windows x 2^window affine records, 96 B each). */
+EXPORT void ref_fixed_base_table_g1(const uint8_t *point, int window, uint8_t *out_table) {
+    g1_aff g; g1_load(&g, point);
+    int outerc; g1_aff *table = g1_fixed_base_table(&g, window, &outerc);
+    size_t tot = (size_t)outerc << window;
+    for (size_t i = 0; i < tot; i++) g1_store(out_table + 96 * i, &table[i]);
+    free(table);
+}
+
+/* k_i * G1 generator for synthetic bases (fixed-base, fast): out affine m x 96 B */
+EXPORT void ref_g1_generator_muls(const uint8_t *scalars, size_t m, uint8_t *out_aff) {
+    g1_aff g; memcpy(&g.x, FPC_G1_X, 48); memcpy(&g.y, FPC_G1_Y, 48); g.inf = 0;
+    int window = 12, outerc;
+    g1_aff *table = g1_fixed_base_table(&g, window, &outerc);
+    g1_jac *r = (g1_jac *)malloc(sizeof(g1_jac) * (m ? m : 1));
+#pragma omp parallel for schedule(dynamic, 64)
+    for (size_t i = 0; i < m; i++) g1_windowed_mul(&r[i], table, window, outerc, (const uint64_t *)(scalars + 32 * i));
+    g1_aff *a = (g1_aff *)malloc(sizeof(g1_aff) * (m ? m : 1));
+    const size_t CH = 4096;
+#pragma omp parallel for schedule(dynamic, 1)
+    for (size_t c0 = 0; c0 < m; c0 += CH) g1_normalize_batch(a + c0, r + c0, (m - c0 < CH) ? m - c0 : CH);
+    for (size_t i = 0; i < m; i++) g1_store(out_aff + 96 * i, &a[i]);
+    free(a); free(r); free(table);
+}
+EXPORT void ref_g2_generator_muls(const uint8_t *scalars, size_t m, uint8_t *out_aff) {
+    g2_aff g; memcpy(&g.x.c0, FPC_G2_X0, 48); memcpy(&g.x.c1, FPC_G2_X1, 48);
+    memcpy(&g.y.c0, FPC_G2_Y0, 48); memcpy(&g.y.c1, FPC_G2_Y1, 48); g.inf = 0;
+    int window = 10, outerc;
+    g2_aff *table = g2_fixed_base_table(&g, window, &outerc);
+    g2_jac *r = (g2_jac *)malloc(sizeof(g2_jac) * (m ? m : 1));
+#pragma omp parallel for schedule(dynamic, 64)
+    for (size_t i = 0; i < m; i++) g2_windowed_mul(&r[i], table, window, outerc, (const uint64_t *)(scalars + 32 * i));
+    g2_aff *a = (g2_aff *)malloc(sizeof(g2_aff) * (m ? m : 1));
+    const size_t CH = 4096;
+#pragma omp parallel for schedule(dynamic, 1)
+    for (size_t c0 = 0; c0 < m; c0 += CH) g2_normalize_batch(a + c0, r + c0, (m - c0 < CH) ? m - c0 : CH);
+    for (size_t i = 0; i < m; i++) g2_store(out_aff + 192 * i, &a[i]);
+    free(a); free(r); free(table);
+}
+
+/* Bls12::multi_miller_loop: identity pairs dropped; chunks of 4 pairs in parallel;
+ * out = Fp12 576 B (c0.c0.c0 ... c1.c2.c1, Montgomery) */
+EXPORT void ref_multi_miller_loop(const uint8_t *g1s, const uint8_t *g2s, size_t k, uint8_t *out_fp12) {
+    g1_aff *ps = (g1_aff *)malloc(sizeof(g1_aff) * (k ? k : 1));
+    ell_coeff *cos = (ell_coeff *)malloc(sizeof(ell_coeff) * N_ELL * (k ? k : 1));
+    size_t m = 0;
+    for (size_t i = 0; i < k; i++) {
+        g1_aff p; g2_aff q; g1_load(&p, g1s + 96 * i); g2_load(&q, g2s + 192 * i);
+        if (p.inf || q.inf) continue;
+        ps[m] = p; g2_prepare(cos + N_ELL * m, &q); m++;
+    }
+    size_t nchunks = (m + 3) / 4;
+    fp12_t *part = (fp12_t *)malloc(sizeof(fp12_t) * (nchunks ? nchunks : 1));
+#pragma omp parallel for schedule(dynamic, 1)
+    for (size_t ch = 0; ch < nchunks; ch++) {
+        size_t lo = ch * 4, hi = lo + 4 < m ? lo + 4 : m;
+        fp12_t f; fp12_set_one(&f);
+        int idx = 0;
+        for (int i = 62; i >= 0; i--) {
+            fp12_sqr(&f, &f);
+            for (size_t j = lo; j < hi; j++) ell(&f, &cos[N_ELL * j + idx], &ps[j]);
+            idx++;
+            if ((BLS_X_ABS >> i) & 1) {
+                for (size_t j = lo; j < hi; j++) ell(&f, &cos[N_ELL * j + idx], &ps[j]);
+                idx++;
+            }
+        }
+        part[ch] = f;
+    }
+    fp12_t f; fp12_set_one(&f);
+    for (size_t ch = 0; ch < nchunks; ch++) fp12_mul(&f, &f, &part[ch]);
+    fp12_conj(&f, &f);
+    memcpy(out_fp12, &f, 576);
+    free(part); free(cos); free(ps);
+}
+
+/* Bls12::final_exponentiation: returns 0 (None) iff input is zero */
+EXPORT int ref_final_exp(const uint8_t *in_fp12, uint8_t *out_fp12) {
+    fp12_t f; memcpy(&f, in_fp12, 576);
+    if (fp12_is_zero(&f)) return 0;
+    fp12_t f1, f2, r, y0, y1, y2;
+    fp12_conj(&f1, &f);
+    fp12_inv(&f2, &f);
+    fp12_mul(&r, &f1, &f2);
+    f2 = r;
+    fp12_frobenius(&r, &r, 2);
+    fp12_mul(&r, &r, &f2);
+    fp12_sqr(&y0, &r);
+    fp12_exp_by_x(&y1, &r);
+    fp12_conj(&y2, &r);
+    fp12_mul(&y1, &y1, &y2);
+    fp12_exp_by_x(&y2, &y1);
+    fp12_conj(&y1, &y1);
+    fp12_mul(&y1, &y1, &y2);
+    fp12_exp_by_x(&y2, &y1);
+    fp12_frobenius(&y1, &y1, 1);
+    fp12_mul(&y1, &y1, &y2);
+    fp12_mul(&r, &r, &y0);
+    fp12_exp_by_x(&y0, &y1);
+    fp12_exp_by_x(&y2, &y0);
+    fp12_frobenius(&y0, &y1, 2);
+    fp12_conj(&y1, &y1);
+    fp12_mul(&y1, &y1, &y2);
+    fp12_mul(&y1, &y1, &y0);
+    fp12_mul(&r, &r, &y1);
+    memcpy(out_fp12, &r, 576);
+    return 1;
+}
+
+EXPORT void ref_fp12_mul(const uint8_t *a, const uint8_t *b, uint8_t *out) {
+    fp12_t x, y, r; memcpy(&x, a, 576); memcpy(&y, b, 576); fp12_mul(&r, &x, &y); memcpy(out, &r, 576);
+}
+/* GT exponentiation by a canonical 256-bit integer (PairingOutput::mul_bigint) */
+EXPORT void ref_fp12_pow(const uint8_t *a, const uint8_t *scalar, uint8_t *out) {
+    fp12_t x, acc; memcpy(&x, a, 576); fp12_set_one(&acc);
+    const uint64_t *s = (const uint64_t *)scalar;
+    for (int i = 255; i >= 0; i--) { fp12_sqr(&acc, &acc); if ((s[i >> 6] >> (i & 63)) & 1) fp12_mul(&acc, &acc, &x); }
+    memcpy(out, &acc, 576);
+}
+EXPORT void ref_fp12_one(uint8_t *out) { fp12_t o; fp12_set_one(&o); memcpy(out, &o, 576); }
+
+/* Fp helpers for tests (Montgomery in/out) */
+EXPORT void ref_fp_mul(const uint8_t *a, const uint8_t *b, uint8_t *out) {
+    fp_t x, y, r; memcpy(&x, a, 48); memcpy(&y, b, 48); fp_mul(&r, &x, &y); memcpy(out, &r, 48);
+}
+EXPORT void ref_fp_inv(const uint8_t *a, uint8_t *out) { fp_t x, r; memcpy(&x, a, 48); fp_inv(&r, &x); memcpy(out, &r, 48); }
