@@ -1,0 +1,167 @@
+// Host wrappers (staging + launches) for the batch group operations; instantiated for G1 in
+// batch_g1.cu and G2 in batch_g2.cu.
+#pragma once
+#include "batch_kernels.cuh"
+
+namespace dg {
+
+static inline int ln_without_floats(size_t n) { int l = 0; while (((size_t)1 << l) < n) l++; return l * 69 / 100; }
+// ark FixedBase::get_mul_window_size, the rule utils::msm::WindowTable::new applies (utils/src/msm.rs:20)
+static inline int fixed_base_window(size_t n) { return n < 32 ? 3 : ln_without_floats(n); }
+
+template <class F> struct Sizes { static constexpr size_t AFF = 2 * sizeof(F), JAC = 3 * sizeof(F); };
+
+template <class F> static int32_t normalize_device(const Jac<F> *d_in, size_t m, Affine<F> *d_out, F *d_prefix, cudaStream_t s) {
+    if (m == 0) return DG_OK;
+    DG_LAUNCH(k_normalize<F>, div_up(div_up(m, DG_NORM_CHUNK), 128), 128, 0, s, d_in, (uint32_t)m, d_out, d_prefix);
+    return DG_OK;
+}
+
+template <class F> static int32_t fixed_table_build(const uint8_t *point, size_t hint_n, uint64_t *handle) {
+    int32_t rc = check_init();
+    if (rc) return rc;
+    if (!point || !handle) return fail(DG_ERR_BAD_ARG, "fixed_base_table: null pointer");
+    ThreadState &t = tls();
+    int window = fixed_base_window(hint_n);
+    int outerc = (255 + window - 1) / window;
+    size_t total = (size_t)outerc << window;
+    size_t need = Arena::pad(Sizes<F>::AFF) + Arena::pad(Sizes<F>::JAC * outerc) + Arena::pad(Sizes<F>::JAC * total) +
+                  Arena::pad(sizeof(F) * total);
+    rc = t.arena.ensure(need, t.stream);
+    if (rc) return rc;
+    Affine<F> *d_g = t.arena.alloc<Affine<F>>(1);
+    Jac<F> *d_outer = t.arena.alloc<Jac<F>>(outerc);
+    Jac<F> *d_rows = t.arena.alloc<Jac<F>>(total);
+    F *d_prefix = t.arena.alloc<F>(total);
+    Affine<F> *d_table = nullptr;
+    DG_CUDA(cudaMalloc(&d_table, Sizes<F>::AFF * total));
+    cudaError_t e = cudaMemcpyAsync(d_g, point, Sizes<F>::AFF, cudaMemcpyHostToDevice, t.stream);
+    if (e != cudaSuccess) { cudaFree(d_table); return fail(DG_ERR_CUDA, cudaGetErrorString(e)); }
+    DG_LAUNCH(k_fixed_outer<F>, 1, 32, 0, t.stream, d_g, window, outerc, d_outer);
+    DG_LAUNCH(k_fixed_rows<F>, div_up(total, 128), 128, 0, t.stream, d_outer, window, outerc, d_rows);
+    normalize_device<F>(d_rows, total, d_table, d_prefix, t.stream);
+    e = cudaStreamSynchronize(t.stream);
+    if (e != cudaSuccess) { cudaFree(d_table); return fail(DG_ERR_CUDA, cudaGetErrorString(e)); }
+    std::lock_guard<std::mutex> lk(ctx().mu);
+    uint64_t h = ctx().next_handle++;
+    HandleRec r;
+    r.kind = sizeof(F) == 48 ? HandleRec::TABLE_G1 : HandleRec::TABLE_G2;
+    r.dev = d_table; r.n = total; r.window = window; r.nwin = outerc;
+    ctx().handles[h] = r;
+    *handle = h;
+    return DG_OK;
+}
+
+template <class F> static int32_t lookup_table(uint64_t handle, HandleRec &out) {
+    std::lock_guard<std::mutex> lk(ctx().mu);
+    auto it = ctx().handles.find(handle);
+    if (it == ctx().handles.end() || it->second.kind != (sizeof(F) == 48 ? HandleRec::TABLE_G1 : HandleRec::TABLE_G2))
+        return fail(DG_ERR_BAD_ARG, "bad fixed-base table handle");
+    out = it->second;
+    return DG_OK;
+}
+
+template <class F> static int32_t fixed_mul_many(uint64_t handle, const uint8_t *scalars, size_t m, uint8_t *out_jac) {
+    int32_t rc = check_init();
+    if (rc) return rc;
+    if (m && (!scalars || !out_jac)) return fail(DG_ERR_BAD_ARG, "fixed_base_mul_many: null pointer");
+    HandleRec tb;
+    rc = lookup_table<F>(handle, tb);
+    if (rc) return rc;
+    if (m == 0) return DG_OK;
+    ThreadState &t = tls();
+    rc = t.arena.ensure(Arena::pad(32 * m) + Arena::pad(Sizes<F>::JAC * m), t.stream);
+    if (rc) return rc;
+    uint8_t *d_s = t.arena.alloc<uint8_t>(32 * m);
+    Jac<F> *d_o = t.arena.alloc<Jac<F>>(m);
+    DG_CUDA(cudaMemcpyAsync(d_s, scalars, 32 * m, cudaMemcpyHostToDevice, t.stream));
+    DG_LAUNCH(k_fixed_mul_many<F>, div_up(m, 128), 128, 0, t.stream, (const Affine<F> *)tb.dev, tb.window, tb.nwin, d_s,
+              (uint32_t)m, d_o);
+    DG_CUDA(cudaMemcpyAsync(out_jac, d_o, Sizes<F>::JAC * m, cudaMemcpyDeviceToHost, t.stream));
+    DG_CUDA(cudaStreamSynchronize(t.stream));
+    return DG_OK;
+}
+
+template <class F> static int32_t batch_mul(const uint8_t *points, const uint8_t *scalars, size_t m, uint8_t *out_jac) {
+    int32_t rc = check_init();
+    if (rc) return rc;
+    if (m && (!points || !scalars || !out_jac)) return fail(DG_ERR_BAD_ARG, "batch_mul: null pointer");
+    if (m == 0) return DG_OK;
+    ThreadState &t = tls();
+    rc = t.arena.ensure(Arena::pad(Sizes<F>::AFF * m) + Arena::pad(32 * m) + Arena::pad(Sizes<F>::JAC * m), t.stream);
+    if (rc) return rc;
+    Affine<F> *d_p = t.arena.alloc<Affine<F>>(m);
+    uint8_t *d_s = t.arena.alloc<uint8_t>(32 * m);
+    Jac<F> *d_o = t.arena.alloc<Jac<F>>(m);
+    DG_CUDA(cudaMemcpyAsync(d_p, points, Sizes<F>::AFF * m, cudaMemcpyHostToDevice, t.stream));
+    DG_CUDA(cudaMemcpyAsync(d_s, scalars, 32 * m, cudaMemcpyHostToDevice, t.stream));
+    DG_LAUNCH(k_batch_mul<F>, div_up(m, 128), 128, 0, t.stream, d_p, d_s, (uint32_t)m, d_o);
+    DG_CUDA(cudaMemcpyAsync(out_jac, d_o, Sizes<F>::JAC * m, cudaMemcpyDeviceToHost, t.stream));
+    DG_CUDA(cudaStreamSynchronize(t.stream));
+    return DG_OK;
+}
+
+template <class F>
+static int32_t batch_mul_add_fixed(const uint8_t *points, const uint8_t *sa, uint64_t handle, const uint8_t *sb, size_t m,
+                                   uint8_t *out_affine) {
+    int32_t rc = check_init();
+    if (rc) return rc;
+    if (m && (!points || !sa || !sb || !out_affine)) return fail(DG_ERR_BAD_ARG, "batch_mul_add_fixed: null pointer");
+    HandleRec tb;
+    rc = lookup_table<F>(handle, tb);
+    if (rc) return rc;
+    if (m == 0) return DG_OK;
+    ThreadState &t = tls();
+    rc = t.arena.ensure(2 * Arena::pad(Sizes<F>::AFF * m) + 2 * Arena::pad(32 * m) + Arena::pad(Sizes<F>::JAC * m) +
+                            Arena::pad(sizeof(F) * m), t.stream);
+    if (rc) return rc;
+    Affine<F> *d_p = t.arena.alloc<Affine<F>>(m);
+    Affine<F> *d_a = t.arena.alloc<Affine<F>>(m);
+    uint8_t *d_sa = t.arena.alloc<uint8_t>(32 * m), *d_sb = t.arena.alloc<uint8_t>(32 * m);
+    Jac<F> *d_o = t.arena.alloc<Jac<F>>(m);
+    F *d_prefix = t.arena.alloc<F>(m);
+    DG_CUDA(cudaMemcpyAsync(d_p, points, Sizes<F>::AFF * m, cudaMemcpyHostToDevice, t.stream));
+    DG_CUDA(cudaMemcpyAsync(d_sa, sa, 32 * m, cudaMemcpyHostToDevice, t.stream));
+    DG_CUDA(cudaMemcpyAsync(d_sb, sb, 32 * m, cudaMemcpyHostToDevice, t.stream));
+    DG_LAUNCH(k_batch_mul_add_fixed<F>, div_up(m, 128), 128, 0, t.stream, d_p, d_sa, (const Affine<F> *)tb.dev, tb.window,
+              tb.nwin, d_sb, (uint32_t)m, d_o);
+    normalize_device<F>(d_o, m, d_a, d_prefix, t.stream);
+    DG_CUDA(cudaMemcpyAsync(out_affine, d_a, Sizes<F>::AFF * m, cudaMemcpyDeviceToHost, t.stream));
+    DG_CUDA(cudaStreamSynchronize(t.stream));
+    return DG_OK;
+}
+
+template <class F> static int32_t normalize_host(const uint8_t *jac, size_t m, uint8_t *out_affine) {
+    int32_t rc = check_init();
+    if (rc) return rc;
+    if (m && (!jac || !out_affine)) return fail(DG_ERR_BAD_ARG, "normalize_batch: null pointer");
+    if (m == 0) return DG_OK;
+    ThreadState &t = tls();
+    rc = t.arena.ensure(Arena::pad(Sizes<F>::JAC * m) + Arena::pad(Sizes<F>::AFF * m) + Arena::pad(sizeof(F) * m), t.stream);
+    if (rc) return rc;
+    Jac<F> *d_in = t.arena.alloc<Jac<F>>(m);
+    Affine<F> *d_out = t.arena.alloc<Affine<F>>(m);
+    F *d_prefix = t.arena.alloc<F>(m);
+    DG_CUDA(cudaMemcpyAsync(d_in, jac, Sizes<F>::JAC * m, cudaMemcpyHostToDevice, t.stream));
+    normalize_device<F>(d_in, m, d_out, d_prefix, t.stream);
+    DG_CUDA(cudaMemcpyAsync(out_affine, d_out, Sizes<F>::AFF * m, cudaMemcpyDeviceToHost, t.stream));
+    DG_CUDA(cudaStreamSynchronize(t.stream));
+    return DG_OK;
+}
+
+template <class F> static int32_t fold_host(const uint8_t *jac, size_t k, uint8_t *out_jac) {
+    int32_t rc = check_init();
+    if (rc) return rc;
+    if (!out_jac || (k && !jac)) return fail(DG_ERR_BAD_ARG, "fold: null pointer");
+    ThreadState &t = tls();
+    rc = t.arena.ensure(Arena::pad(Sizes<F>::JAC * (k + 1)), t.stream);
+    if (rc) return rc;
+    Jac<F> *d = t.arena.alloc<Jac<F>>(k + 1);
+    if (k) DG_CUDA(cudaMemcpyAsync(d + 1, jac, Sizes<F>::JAC * k, cudaMemcpyHostToDevice, t.stream));
+    DG_LAUNCH(k_fold_jac<F>, 1, 32, 0, t.stream, d + 1, (uint32_t)k, d);
+    DG_CUDA(cudaMemcpyAsync(out_jac, d, Sizes<F>::JAC, cudaMemcpyDeviceToHost, t.stream));
+    DG_CUDA(cudaStreamSynchronize(t.stream));
+    return DG_OK;
+}
+
+}  // namespace dg

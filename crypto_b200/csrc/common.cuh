@@ -1,0 +1,89 @@
+// Host-side plumbing shared by the translation units of libdockgpu.so: error reporting,
+// per-thread stream + scratch arena (the C ABI is re-entrant from rayon-style worker threads,
+// SURVEY.md 8b "Threading"), handle table, launch counter.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <atomic>
+#include <mutex>
+#include <string>
+#include <unordered_map>
+#include <vector>
+#include "../../include/dockgpu.h"
+
+namespace dg {
+
+struct HandleRec {
+    enum Kind { BASES_G1, BASES_G2, TABLE_G1, TABLE_G2 } kind;
+    void *dev = nullptr;
+    size_t n = 0;            // bases: point count; tables: total records
+    int window = 0, nwin = 0;
+};
+
+struct Context {
+    std::mutex mu;
+    bool inited = false;
+    int device = 0;
+    int sm_count = 148;
+    std::unordered_map<uint64_t, HandleRec> handles;
+    uint64_t next_handle = 1;
+    std::atomic<uint64_t> launches{0};
+    std::atomic<int> msm_window_override{0};
+};
+Context &ctx();
+
+// Grow-only device scratch; contents are zeroed before release because scalars may be secret
+// material (vb_accumulator/src/positive.rs:349-352 zeroizes them on the CPU side).
+struct Arena {
+    char *base = nullptr;
+    size_t cap = 0, used = 0;
+    int32_t ensure(size_t bytes, cudaStream_t s);
+    void reset() { used = 0; }
+    template <class T> T *alloc(size_t count) {
+        size_t bytes = (count * sizeof(T) + 255) & ~(size_t)255;
+        char *p = base + used;
+        used += bytes;
+        return reinterpret_cast<T *>(p);
+    }
+    static size_t pad(size_t bytes) { return (bytes + 255) & ~(size_t)255; }
+    void release();
+};
+
+struct ThreadState {
+    cudaStream_t stream = nullptr;
+    Arena arena;
+    std::string err;
+    uint32_t *err_flag = nullptr;     // device word the kernels OR error bits into
+    uint32_t *err_flag_host = nullptr;  // pinned mirror
+    ~ThreadState();
+};
+ThreadState &tls();
+
+int32_t fail(int32_t code, const std::string &msg);
+int32_t check_init();
+
+#define DG_CUDA(call)                                                                              \
+    do {                                                                                           \
+        cudaError_t e_ = (call);                                                                   \
+        if (e_ != cudaSuccess)                                                                     \
+            return dg::fail(e_ == cudaErrorMemoryAllocation ? DG_ERR_OOM : DG_ERR_CUDA,            \
+                            std::string(#call) + ": " + cudaGetErrorString(e_));                   \
+    } while (0)
+
+#define DG_LAUNCH(kernel, grid, block, smem, stream, ...)                                          \
+    do {                                                                                           \
+        kernel<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__);                                \
+        dg::ctx().launches.fetch_add(1, std::memory_order_relaxed);                                \
+    } while (0)
+
+static inline unsigned div_up(size_t a, size_t b) { return (unsigned)((a + b - 1) / b); }
+
+// ---- internal entry points implemented per translation unit (device pointers, async) ----------
+size_t msm_scratch_bytes_g1(size_t n);
+size_t msm_scratch_bytes_g2(size_t n);
+int32_t msm_run_g1(const void *bases_dev, const void *scalars_dev, size_t n, void *out_jac_dev, char *scratch,
+                   uint32_t *err_flag, cudaStream_t s);
+int32_t msm_run_g2(const void *bases_dev, const void *scalars_dev, size_t n, void *out_jac_dev, char *scratch,
+                   uint32_t *err_flag, cudaStream_t s);
+
+}  // namespace dg

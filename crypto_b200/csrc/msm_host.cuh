@@ -1,0 +1,121 @@
+// Host-side launch sequence of the Pippenger pipeline (see msm_kernels.cuh); included by
+// msm_g1.cu and msm_g2.cu which instantiate it for Fp and Fp2.
+#pragma once
+#include "common.cuh"
+#include "msm_kernels.cuh"
+
+namespace dg {
+
+static inline int ceil_log2_sz(size_t n) { int l = 0; while (((size_t)1 << l) < n) l++; return l; }
+
+// Window bits: about log2(n) - 4 so that an average bucket receives ~32 points per window,
+// which keeps the bucket reduction (2 * 2^(c-1) full additions per window) near 10 % of the
+// accumulation work.  nwin * c >= 256 so the top signed digit cannot overflow.
+static inline MsmGeom msm_geometry(size_t n) {
+    int c = ctx().msm_window_override.load();
+    if (c <= 0) {
+        c = ceil_log2_sz(n ? n : 1) - 4;
+        if (c < 4) c = 4;
+        if (c > 20) c = 20;
+        if (c == 15) c = 16;          // 16 x 16 = 256 exactly: one window fewer than c = 15
+        if (c == 14) c = 13;          // 20 windows instead of 19 but half the buckets
+    }
+    MsmGeom g;
+    g.c = c;
+    g.nwin = (256 + c - 1) / c;
+    g.nbw = 1u << (c - 1);
+    g.nb = g.nbw * (uint32_t)g.nwin;
+    return g;
+}
+
+struct MsmLayout {
+    MsmGeom g;
+    uint32_t L, nchunks, ngroups1;
+    size_t o_hist, o_off, o_cursor, o_bsums, o_entries, o_buckets, o_head, o_tail, o_red[4], total;
+};
+
+template <class F> static inline MsmLayout msm_layout(size_t n) {
+    MsmLayout m;
+    m.g = msm_geometry(n);
+    size_t max_entries = n * (size_t)m.g.nwin;
+    size_t threads_target = (size_t)ctx().sm_count * 384 * 4;
+    size_t L = (max_entries + threads_target - 1) / threads_target;
+    if (L < 8) L = 8;
+    if (L > 512) L = 512;
+    m.L = (uint32_t)L;
+    m.nchunks = (uint32_t)((max_entries + L - 1) / L);
+    if (m.nchunks == 0) m.nchunks = 1;
+    int log_g1 = m.g.nbw >= 4096 ? 4 : 3;
+    m.ngroups1 = (m.g.nbw + (1u << log_g1) - 1) >> log_g1;
+    size_t o = 0;
+    auto take = [&](size_t bytes) { size_t r = o; o += Arena::pad(bytes); return r; };
+    m.o_hist = take(sizeof(uint32_t) * m.g.nb);
+    m.o_off = take(sizeof(uint32_t) * ((size_t)m.g.nb + 1));
+    m.o_cursor = take(sizeof(uint32_t) * m.g.nb);
+    m.o_bsums = take(sizeof(uint32_t) * (m.g.nb / DG_SCAN_ITEMS + 2));
+    m.o_entries = take(sizeof(uint32_t) * (max_entries ? max_entries : 1));
+    m.o_buckets = take(sizeof(XYZZ<F>) * m.g.nb);
+    m.o_head = take(sizeof(XYZZ<F>) * m.nchunks);
+    m.o_tail = take(sizeof(XYZZ<F>) * m.nchunks);
+    for (int k = 0; k < 4; k++) m.o_red[k] = take(sizeof(XYZZ<F>) * (size_t)m.g.nwin * m.ngroups1);
+    m.total = o;
+    return m;
+}
+
+template <class F> __global__ void k_set_jac_inf(Jac<F> *out) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) jac_store(out, jac_inf<F>());
+}
+
+template <class F>
+static int32_t msm_run(const void *bases_dev, const void *scalars_dev, size_t n, void *out_jac_dev, char *scratch,
+                       uint32_t *err_flag, cudaStream_t s) {
+    if (n == 0) {
+        DG_LAUNCH(k_set_jac_inf<F>, 1, 32, 0, s, (Jac<F> *)out_jac_dev);
+        return DG_OK;
+    }
+    if (n >= (1ull << 31)) return fail(DG_ERR_BAD_ARG, "msm: n must be < 2^31");
+    MsmLayout m = msm_layout<F>(n);
+    const MsmGeom g = m.g;
+    uint32_t *hist = (uint32_t *)(scratch + m.o_hist), *off = (uint32_t *)(scratch + m.o_off);
+    uint32_t *cursor = (uint32_t *)(scratch + m.o_cursor), *bsums = (uint32_t *)(scratch + m.o_bsums);
+    uint32_t *entries = (uint32_t *)(scratch + m.o_entries);
+    XYZZ<F> *buckets = (XYZZ<F> *)(scratch + m.o_buckets), *head = (XYZZ<F> *)(scratch + m.o_head);
+    XYZZ<F> *tail = (XYZZ<F> *)(scratch + m.o_tail);
+    XYZZ<F> *red[4];
+    for (int k = 0; k < 4; k++) red[k] = (XYZZ<F> *)(scratch + m.o_red[k]);
+
+    DG_CUDA(cudaMemsetAsync(hist, 0, sizeof(uint32_t) * g.nb, s));
+    unsigned gd = div_up(n, 256);
+    DG_LAUNCH(k_digits<0>, gd, 256, 0, s, (const uint32_t *)scalars_dev, (uint32_t)n, g, hist, (uint32_t *)nullptr, err_flag);
+    unsigned sb = div_up(g.nb, DG_SCAN_ITEMS);
+    DG_LAUNCH(k_scan_blocks, sb, 1024, 0, s, hist, off, bsums, g.nb);
+    DG_LAUNCH(k_scan_sums, 1, 1024, 0, s, bsums, sb);
+    DG_LAUNCH(k_scan_add, sb, 1024, 0, s, off, bsums, hist, g.nb, cursor);
+    DG_LAUNCH(k_digits<1>, gd, 256, 0, s, (const uint32_t *)scalars_dev, (uint32_t)n, g, cursor, entries, err_flag);
+
+    DG_LAUNCH(k_accumulate<F>, div_up(m.nchunks, 128), 128, 0, s, (const Affine<F> *)bases_dev, entries, off, g.nb, m.L,
+              buckets, head, tail);
+    DG_LAUNCH(k_bucket_fixup<F>, div_up(g.nb, 128), 128, 0, s, off, g.nb, m.L, buckets, head, tail);
+
+    // multi-level bucket reduction
+    const XYZZ<F> *x = buckets, *y = nullptr;
+    uint32_t cnt_x = g.nbw, cnt_y = 0, stride_x = g.nbw, stride_y = 0;
+    int pp = 0;
+    const XYZZ<F> *wsum = nullptr;
+    for (int level = 0;; level++) {
+        int log_g = (level == 0 && g.nbw >= 4096) ? 4 : 3;
+        uint32_t cnt = cnt_x > cnt_y ? cnt_x : cnt_y;
+        uint32_t ngroups = (cnt + (1u << log_g) - 1) >> log_g;
+        XYZZ<F> *xo = red[2 * pp], *yo = red[2 * pp + 1];
+        DG_LAUNCH(k_reduce_level<F>, div_up((size_t)ngroups * g.nwin, 128), 128, 0, s, x, cnt_x, stride_x, y, cnt_y, stride_y,
+                  log_g, ngroups, g.nwin, xo, yo, m.ngroups1);
+        if (ngroups == 1) { wsum = yo; break; }
+        x = xo; y = yo; cnt_x = ngroups - 1; cnt_y = ngroups; stride_x = stride_y = m.ngroups1;
+        pp ^= 1;
+    }
+    DG_LAUNCH(k_window_combine<F>, 1, 32, 0, s, wsum, m.ngroups1, g.nwin, g.c, (Jac<F> *)out_jac_dev);
+    DG_CUDA(cudaGetLastError());
+    return DG_OK;
+}
+
+}  // namespace dg

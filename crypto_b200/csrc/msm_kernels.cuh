@@ -1,0 +1,245 @@
+// Pippenger multi-scalar multiplication on sm_100a, templated over the base field (G1: Fp,
+// G2: Fp2).  Replaces ark-ec 0.4 VariableBaseMSM::msm_bigint as the reference calls it
+// (legogroth16/src/prover.rs:286,299,363,592; bbs_plus/src/setup.rs:145;
+// schnorr_pok/src/pok_generalized_pedersen.rs:97,153; vb_accumulator/src/witness.rs:415; ...
+// SURVEY.md 8a rows a4/a5).
+//
+// Pipeline (all on one stream, no host round trip):
+//   1 k_digits<COUNT>   signed radix-2^c digits of every scalar, per-(window,bucket) histogram
+//   2 k_scan_*          exclusive prefix sum of the histogram -> bucket offsets
+//   3 k_digits<SCATTER> counting-sort the (point index, sign) entries by (window, bucket)
+//   4 k_accumulate      perfectly balanced segmented accumulation: every thread folds a
+//                       fixed-length chunk of the sorted entry list into XYZZ partial sums
+//                       (run time independent of the scalar distribution - witnesses full of
+//                       0/1 values do not serialise on hot buckets)
+//   5 k_bucket_fixup    stitches the partial sums of buckets that straddle chunks
+//   6 k_reduce_level    multi-level weighted running-sum  sum_b b*B[w][b]  per window
+//   7 k_window_combine  Horner over windows, result as Jacobian (ark Projective layout)
+#pragma once
+#include "ec.cuh"
+
+namespace dg {
+
+struct MsmGeom {
+    int c;            // window bits
+    int nwin;         // number of windows, nwin * c >= 256 so the top signed digit never overflows
+    uint32_t nbw;     // buckets per window = 2^(c-1)
+    uint32_t nb;      // total buckets = nwin * nbw
+};
+
+// ---------------------------------------------------------------- digits / counting sort -----
+template <int PASS>   // 0 = count, 1 = scatter
+__global__ void __launch_bounds__(256) k_digits(const uint32_t *__restrict__ scalars, uint32_t n, MsmGeom g,
+                                                uint32_t *__restrict__ counters, uint32_t *__restrict__ entries,
+                                                uint32_t *__restrict__ err_flag) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint4 *sp = reinterpret_cast<const uint4 *>(scalars) + 2 * (size_t)i;
+    uint4 lo = __ldg(sp), hi = __ldg(sp + 1);
+    uint32_t s[9] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w, 0};
+    const uint32_t mask = (1u << g.c) - 1, half = 1u << (g.c - 1);
+    uint32_t carry = 0;
+    for (int w = 0; w < g.nwin; w++) {
+        int bit = w * g.c;
+        uint32_t raw = 0;
+        if (bit < 256) {
+            int word = bit >> 5, off = bit & 31;
+            uint64_t two = ((uint64_t)s[word + 1] << 32) | s[word];
+            raw = (uint32_t)(two >> off) & mask;
+        }
+        uint32_t d = raw + carry;
+        bool neg = d > half;
+        carry = neg ? 1u : 0u;
+        uint32_t mag = neg ? (1u << g.c) - d : d;
+        if (mag != 0) {
+            uint32_t bucket = w * g.nbw + mag - 1;
+            if (PASS == 0) {
+                atomicAdd(&counters[bucket], 1u);
+            } else {
+                uint32_t pos = atomicAdd(&counters[bucket], 1u);
+                entries[pos] = i | (neg ? 0x80000000u : 0u);
+            }
+        }
+    }
+    if (PASS == 0 && carry) atomicOr(err_flag, 1u);   // scalar >= 2^(nwin*c - 1): not a canonical Fr
+}
+
+// exclusive scan of `in[0..n)` into `out[0..n]` (out[n] = total); 3 small kernels, 4096 items/block
+#define DG_SCAN_ITEMS 4096
+static __global__ void __launch_bounds__(1024) k_scan_blocks(const uint32_t *__restrict__ in, uint32_t *__restrict__ out,
+                                                      uint32_t *__restrict__ block_sums, uint32_t n) {
+    __shared__ uint32_t warp_tot[32];
+    uint32_t base = blockIdx.x * DG_SCAN_ITEMS + threadIdx.x * 4;
+    uint32_t v[4], sum = 0;
+#pragma unroll
+    for (int k = 0; k < 4; k++) { v[k] = (base + k < n) ? in[base + k] : 0; sum += v[k]; }
+    uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    uint32_t incl = sum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { uint32_t t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
+    if (lane == 31) warp_tot[wid] = incl;
+    __syncthreads();
+    if (wid == 0) {
+        uint32_t t = warp_tot[lane], inc = t;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { uint32_t u = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += u; }
+        warp_tot[lane] = inc - t;
+        if (lane == 31) block_sums[blockIdx.x] = inc;
+    }
+    __syncthreads();
+    uint32_t excl = warp_tot[wid] + incl - sum;
+#pragma unroll
+    for (int k = 0; k < 4; k++) { if (base + k < n) out[base + k] = excl; excl += v[k]; }
+}
+static __global__ void __launch_bounds__(1024) k_scan_sums(uint32_t *block_sums, uint32_t nblocks) {
+    // single block; serial over tiles of 1024
+    __shared__ uint32_t warp_tot[32];
+    __shared__ uint32_t running;
+    if (threadIdx.x == 0) running = 0;
+    __syncthreads();
+    uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    for (uint32_t t0 = 0; t0 < nblocks; t0 += 1024) {
+        uint32_t i = t0 + threadIdx.x;
+        uint32_t v = i < nblocks ? block_sums[i] : 0, incl = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { uint32_t t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
+        if (lane == 31) warp_tot[wid] = incl;
+        __syncthreads();
+        if (wid == 0) {
+            uint32_t t = warp_tot[lane], inc = t;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { uint32_t u = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += u; }
+            warp_tot[lane] = inc - t;
+        }
+        __syncthreads();
+        uint32_t excl = running + warp_tot[wid] + incl - v;
+        if (i < nblocks) block_sums[i] = excl;
+        __syncthreads();
+        if (threadIdx.x == 1023) running = excl + v;
+        __syncthreads();
+    }
+}
+static __global__ void __launch_bounds__(1024) k_scan_add(uint32_t *__restrict__ out, const uint32_t *__restrict__ block_sums,
+                                                   const uint32_t *__restrict__ in, uint32_t n, uint32_t *__restrict__ copy) {
+    uint32_t base = blockIdx.x * DG_SCAN_ITEMS + threadIdx.x * 4, add = block_sums[blockIdx.x];
+#pragma unroll
+    for (int k = 0; k < 4; k++)
+        if (base + k < n) {
+            uint32_t v = out[base + k] + add;
+            out[base + k] = v;
+            copy[base + k] = v;
+            if (base + k == n - 1) out[n] = v + in[n - 1];
+        }
+}
+
+// ---------------------------------------------------------------- bucket accumulation --------
+// entries[] is sorted by bucket; off[b] .. off[b+1] is bucket b's slice; M = off[nb].
+// Thread t owns entries [t*L, (t+1)*L).  Runs (maximal same-bucket stretches inside the chunk):
+//   first run of the chunk  -> head[t]       last run (if not also first) -> tail[t]
+//   runs strictly inside    -> buckets[b] directly (nobody else touches that bucket)
+template <class F>
+__global__ void __launch_bounds__(128, 3) k_accumulate(const Affine<F> *__restrict__ bases, const uint32_t *__restrict__ entries,
+                                                       const uint32_t *__restrict__ off, uint32_t nb, uint32_t L,
+                                                       XYZZ<F> *__restrict__ buckets, XYZZ<F> *__restrict__ head,
+                                                       XYZZ<F> *__restrict__ tail) {
+    uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    uint32_t M = off[nb];
+    uint64_t start64 = (uint64_t)t * L;
+    if (start64 >= M) return;
+    uint32_t start = (uint32_t)start64;
+    uint32_t end = (M - start > L) ? start + L : M;
+    // bucket containing `start`: largest b with off[b] <= start  (and off[b+1] > start)
+    uint32_t lo = 0, hi = nb;            // invariant off[lo] <= start < off[hi]
+    while (hi - lo > 1) {
+        uint32_t mid = (lo + hi) >> 1;
+        if (off[mid] <= start) lo = mid; else hi = mid;
+    }
+    uint32_t b = lo, bend = off[b + 1];
+    XYZZ<F> acc = xyzz_inf<F>();
+    bool first = true;
+    for (uint32_t e = start; e < end; e++) {
+        if (e == bend) {
+            if (first) xyzz_store(&head[t], acc); else xyzz_store(&buckets[b], acc);
+            first = false;
+            acc = xyzz_inf<F>();
+            do { b++; bend = off[b + 1]; } while (bend <= e);
+        }
+        uint32_t ent = __ldg(&entries[e]);
+        Affine<F> p = aff_load<F>(&bases[ent & 0x7fffffffu]);
+        p.y = fcneg(p.y, (ent >> 31) != 0);
+        acc = xyzz_madd(acc, p);
+    }
+    if (first) xyzz_store(&head[t], acc); else xyzz_store(&tail[t], acc);
+}
+
+template <class F>
+__global__ void __launch_bounds__(128) k_bucket_fixup(const uint32_t *__restrict__ off, uint32_t nb, uint32_t L,
+                                                      XYZZ<F> *__restrict__ buckets, const XYZZ<F> *__restrict__ head,
+                                                      const XYZZ<F> *__restrict__ tail) {
+    uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= nb) return;
+    uint32_t s = off[b], e = off[b + 1], M = off[nb];
+    if (s == e) { xyzz_store(&buckets[b], xyzz_inf<F>()); return; }
+    uint32_t t0 = s / L, t1 = (e - 1) / L;
+    bool first0 = (s == t0 * L);
+    if (t0 == t1) {
+        uint64_t cend = (uint64_t)(t0 + 1) * L;
+        bool last0 = (e == (cend < M ? (uint32_t)cend : M));
+        if (first0) xyzz_store(&buckets[b], xyzz_load<F>(&head[t0]));
+        else if (last0) xyzz_store(&buckets[b], xyzz_load<F>(&tail[t0]));
+        return;                                     // middle run: already written by k_accumulate
+    }
+    XYZZ<F> acc = first0 ? xyzz_load<F>(&head[t0]) : xyzz_load<F>(&tail[t0]);
+    for (uint32_t t = t0 + 1; t <= t1; t++) acc = xyzz_add(acc, xyzz_load<F>(&head[t]));
+    xyzz_store(&buckets[b], acc);
+}
+
+// ---------------------------------------------------------------- bucket reduction -----------
+// One level of  S = sum_j (j+1) x_j + sum_j y_j  per window.  Thread (w, q) folds the g items
+// x[q*g .. q*g+g) with a running sum:  A = sum (k+1) x_{qg+k},  R = sum x_{qg+k},  Y = sum y.
+// Then  S = sum_q (A_q + Y_q) + sum_{q>=1} q * (g R_q):  the next level's y'_q = A_q + Y_q and
+// x'_{q-1} = g * R_q (log2 g doublings).  Items past the end are the identity.
+template <class F>
+__global__ void __launch_bounds__(128) k_reduce_level(const XYZZ<F> *__restrict__ x, uint32_t cnt_x, uint32_t stride_x,
+                                                      const XYZZ<F> *__restrict__ y, uint32_t cnt_y, uint32_t stride_y,
+                                                      int log_g, uint32_t ngroups, int nwin,
+                                                      XYZZ<F> *__restrict__ xo, XYZZ<F> *__restrict__ yo, uint32_t stride_o) {
+    uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
+    if (tid >= ngroups * (uint32_t)nwin) return;
+    uint32_t w = tid / ngroups, q = tid % ngroups, g = 1u << log_g;
+    const XYZZ<F> *xw = x + (size_t)w * stride_x;
+    XYZZ<F> run = xyzz_inf<F>(), acc = xyzz_inf<F>();
+    for (uint32_t k = g; k-- > 0;) {
+        uint32_t j = q * g + k;
+        if (j < cnt_x) run = xyzz_add(run, xyzz_load<F>(&xw[j]));
+        acc = xyzz_add(acc, run);
+    }
+    if (cnt_y) {
+        const XYZZ<F> *yw = y + (size_t)w * stride_y;
+        for (uint32_t k = 0; k < g; k++) {
+            uint32_t j = q * g + k;
+            if (j < cnt_y) acc = xyzz_add(acc, xyzz_load<F>(&yw[j]));
+        }
+    }
+    xyzz_store(&yo[(size_t)w * stride_o + q], acc);
+    if (q >= 1) {
+        for (int k = 0; k < log_g; k++)
+            if (!xyzz_is_inf(run)) run = xyzz_dbl(run);
+        xyzz_store(&xo[(size_t)w * stride_o + q - 1], run);
+    }
+}
+
+// window sums S_w (one XYZZ per window at stride) -> sum_w 2^(c w) S_w, Horner from the top.
+template <class F>
+__global__ void k_window_combine(const XYZZ<F> *__restrict__ wsum, uint32_t stride, int nwin, int c, Jac<F> *out) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    XYZZ<F> acc = xyzz_load<F>(&wsum[(size_t)(nwin - 1) * stride]);
+    for (int w = nwin - 2; w >= 0; w--) {
+        for (int k = 0; k < c; k++)
+            if (!xyzz_is_inf(acc)) acc = xyzz_dbl(acc);
+        acc = xyzz_add(acc, xyzz_load<F>(&wsum[(size_t)w * stride]));
+    }
+    jac_store(out, xyzz_to_jac(acc));
+}
+
+}  // namespace dg

@@ -1,0 +1,605 @@
+// Optimal-ate pairing on BLS12-381 for sm_100a: Miller loop + final exponentiation.
+//
+// Replaces ark_ec::models::bls12::Bls12::{multi_miller_loop, final_exponentiation} as the
+// reference reaches them (bbs_plus/src/proof.rs:494, bbs_plus/src/signature.rs:284,
+// legogroth16/src/verifier.rs:69-80, vb_accumulator/src/positive.rs:420,
+// utils/src/randomized_pairing_check.rs:134,169,204-214).
+//
+// Design: a pairing is a long dependent chain of Fp12 operations, so one thread per pairing
+// would leave the chip idle and take tens of milliseconds.  Instead one 128-thread CTA is a
+// "tower engine": operands live in shared memory, and every Fp12 multiplication is spread over
+// the CTA - 108 lanes each do ONE Fp Montgomery multiplication (36 Fp2 products x 3 Karatsuba
+// parts over the flattened basis Fp12 = Fp2[w]/(w^6 - xi)), 12 lanes recombine.  The G2
+// doubling/addition steps are issued as two waves of independent Fp2 products the same way.
+// The grid has one CTA per pair; partial Miller values are multiplied by a tree of CTAs and
+// one CTA runs the final exponentiation (eprint 2020/875 chain, the arkworks convention:
+// the result is e(P,Q)^3 w.r.t. the textbook exponent (p^12-1)/r).
+//
+// Line functions follow ark-ec 0.4 bls12::G2Prepared (homogeneous projective doubling /
+// addition, M-type twist, ell = mul_by_014(c0, c1*P.x, c2*P.y)), so the Miller-loop value itself
+// is bit-identical to arkworks', not only the pairing.
+#include "common.cuh"
+#include "ec.cuh"
+
+namespace dg {
+
+#define PAIR_THREADS 128
+#define BLS_X_ABS 0xd201000000010000ULL
+
+// Fp12 in shared/global memory: 12 Fp in ark order (c0.c0.c0, c0.c0.c1, c0.c1.c0, ..., c1.c2.c1).
+// Flattened basis: coefficient of w^k (an Fp2) lives at tower position (i = k&1, j = k>>1).
+struct F12 { Fp c[12]; };
+__device__ __forceinline__ int widx(int k) { return (k & 1) * 6 + (k >> 1) * 2; }
+
+static __device__ __noinline__ Fp fp_mul_smem(const Fp *a, const Fp *b) { return fp_mul(*a, *b); }
+
+// One Karatsuba part of an Fp2 product: 0: a0*b0, 1: a1*b1, 2: (a0+a1)*(b0+b1)
+__device__ __forceinline__ Fp fp2_part(int part, const Fp *a, const Fp *b) {
+    if (part == 0) return fp_mul_smem(a, b);
+    if (part == 1) return fp_mul_smem(a + 1, b + 1);
+    Fp sa = fp_add(a[0], a[1]), sb = fp_add(b[0], b[1]);
+    return fp_mul_smem(&sa, &sb);
+}
+// recombine three parts into the Fp2 product
+__device__ __forceinline__ void fp2_from_parts(Fp *d, const Fp *p) {
+    Fp c0 = fp_sub(p[0], p[1]);
+    Fp c1 = fp_sub(fp_sub(p[2], p[0]), p[1]);
+    d[0] = c0; d[1] = c1;
+}
+
+struct Engine {
+    Fp prod[108];      // product scratch
+    Fp tmp[16];        // linear-stage scratch
+};
+
+// C = A * B (C may alias A or B).  All PAIR_THREADS threads must call.
+__device__ void f12_mul(Engine &e, F12 *C, const F12 *A, const F12 *B) {
+    int tid = threadIdx.x;
+    if (tid < 108) {
+        int pr = tid / 3, part = tid - pr * 3, i = pr / 6, j = pr - i * 6;
+        e.prod[tid] = fp2_part(part, &A->c[widx(i)], &B->c[widx(j)]);
+    }
+    __syncthreads();
+    if (tid < 12) {
+        int k = tid >> 1, comp = tid & 1;
+        // T* over i+j = k, U* over i+j = k+6 (w^6 = xi = 1+u)
+        Fp T0 = fp_zero(), T1 = fp_zero(), T2 = fp_zero(), U0 = fp_zero(), U1 = fp_zero(), U2 = fp_zero();
+        for (int i = 0; i < 6; i++) {
+            int j = k - i;
+            if (j >= 0 && j < 6) {
+                const Fp *p = &e.prod[(i * 6 + j) * 3];
+                if (comp == 0) { T0 = fp_add(T0, p[0]); T1 = fp_add(T1, p[1]); }
+                else { T0 = fp_add(T0, fp_add(p[0], p[1])); T2 = fp_add(T2, p[2]); }
+            }
+            j = k + 6 - i;
+            if (j >= 0 && j < 6) {
+                const Fp *p = &e.prod[(i * 6 + j) * 3];
+                if (comp == 0) { U0 = fp_add(U0, p[0]); U2 = fp_add(U2, p[2]); }
+                else { U1 = fp_add(U1, p[1]); U2 = fp_add(U2, p[2]); }
+            }
+        }
+        Fp r;
+        if (comp == 0) r = fp_sub(fp_add(fp_sub(T0, T1), fp_dbl(U0)), U2);      // T0 - T1 + 2 U0 - U2
+        else r = fp_sub(fp_add(fp_sub(T2, T0), U2), fp_dbl(U1));               // T2 - (T0+T1) + U2 - 2 U1
+        C->c[widx(k) + comp] = r;
+    }
+    __syncthreads();
+}
+
+__device__ void f12_copy(F12 *d, const F12 *s) {
+    int tid = threadIdx.x;
+    if (tid < 12) d->c[tid] = s->c[tid];
+    __syncthreads();
+}
+__device__ void f12_set_one(F12 *d) {
+    int tid = threadIdx.x;
+    if (tid < 12) d->c[tid] = tid == 0 ? fp_one() : fp_zero();
+    __syncthreads();
+}
+// conjugation over Fp6 (= p^6 Frobenius): negate the w-odd half (tower c1 = indices 6..11)
+__device__ void f12_conj(F12 *d, const F12 *s) {
+    int tid = threadIdx.x;
+    if (tid < 12) d->c[tid] = tid < 6 ? s->c[tid] : fp_neg(s->c[tid]);
+    __syncthreads();
+}
+// d = s^(p^pw), pw in {1,2,3}: coefficient of w^k -> conj^pw(a_k) * xi^(k (p^pw - 1)/6)
+__device__ void f12_frobenius(Engine &e, F12 *d, const F12 *s, int pw) {
+    int tid = threadIdx.x;
+    if (tid < 18) {
+        int k = tid / 3, part = tid - k * 3;
+        Fp a[2] = {s->c[widx(k)], s->c[widx(k) + 1]};
+        if (pw & 1) a[1] = fp_neg(a[1]);
+        const uint32_t(*g)[2][12] = pw == 1 ? DGC_FROB1 : pw == 2 ? DGC_FROB2 : DGC_FROB3;
+        Fp b[2];
+#pragma unroll
+        for (int t = 0; t < 12; t++) { b[0].l[t] = g[k][0][t]; b[1].l[t] = g[k][1][t]; }
+        e.prod[tid] = fp2_part(part, a, b);
+    }
+    __syncthreads();
+    if (tid < 6) fp2_from_parts(&d->c[widx(tid)], &e.prod[tid * 3]);
+    __syncthreads();
+}
+
+// Fp inversion by one thread (a^(p-2)); the only long serial chain in the final exponentiation
+static __device__ __noinline__ Fp fp_inv_serial(const Fp &a) {
+    Fp tbl[16];
+    tbl[0] = fp_one();
+    tbl[1] = a;
+    for (int i = 2; i < 16; i++) tbl[i] = fp_mul_smem(&tbl[i - 1], &a);
+    uint32_t ex[12];
+#pragma unroll
+    for (int i = 0; i < 12; i++) ex[i] = fp_p_limb(i);
+    ex[0] -= 2;
+    Fp acc = fp_one();
+    for (int nib = 95; nib >= 0; nib--) {
+        for (int k = 0; k < 4; k++) acc = fp_mul_smem(&acc, &acc);
+        uint32_t d = (ex[nib >> 3] >> ((nib & 7) * 4)) & 15;
+        acc = fp_mul_smem(&acc, &tbl[d]);
+    }
+    return acc;
+}
+
+// d = 1/s via norms:  abar = conj(s);  N = s*abar in Fp6;  N^-1 = sigma(N) sigma^2(N) / Norm_{Fp6/Fp2}(N)
+// with sigma = p^2 Frobenius;  the Fp2 norm is inverted with one Fp inversion.
+__device__ void f12_inv(Engine &e, F12 *d, const F12 *s, F12 *t0, F12 *t1, F12 *t2) {
+    int tid = threadIdx.x;
+    f12_conj(t0, s);                 // abar
+    f12_mul(e, t1, s, t0);           // N (odd half is zero)
+    f12_frobenius(e, t2, t1, 2);     // sigma(N)
+    f12_mul(e, t0, t0, t2);          // abar * sigma(N)
+    f12_frobenius(e, t2, t2, 2);     // sigma^2(N)
+    f12_mul(e, t0, t0, t2);          // abar * sigma(N) * sigma^2(N)
+    f12_frobenius(e, t2, t2, 2);     // back to N  (sigma^3 = id on Fp6)
+    f12_frobenius(e, d, t2, 2);      // sigma(N)
+    f12_mul(e, t1, t2, d);           // N sigma(N)
+    f12_frobenius(e, d, d, 2);       // sigma^2(N)
+    f12_mul(e, t1, t1, d);           // Norm in Fp2: only the w^0 coefficient is non-zero
+    if (tid == 0) {
+        Fp x = t1->c[0], y = t1->c[1];
+        Fp n = fp_inv_serial(fp_add(fp_mul(x, x), fp_mul(y, y)));
+        t1->c[0] = fp_mul(x, n);
+        t1->c[1] = fp_neg(fp_mul(y, n));
+    }
+    __syncthreads();
+    f12_mul(e, d, t0, t1);
+}
+
+// d = s^|x| conjugated (x < 0): ark Bls12::exp_by_x.  d must not alias s.
+__device__ void f12_exp_by_x(Engine &e, F12 *d, const F12 *s) {
+    f12_copy(d, s);                                   // top bit (63) of |x|
+    for (int i = 62; i >= 0; i--) {
+        f12_mul(e, d, d, d);
+        if ((BLS_X_ABS >> i) & 1) f12_mul(e, d, d, s);
+    }
+    f12_conj(d, d);
+}
+
+// Bls12::final_exponentiation, same operation order as arkworks; r = in/out, 5 temporaries.
+__device__ void f12_final_exp(Engine &e, F12 *r, F12 *f1, F12 *f2, F12 *y0, F12 *y1, F12 *y2) {
+    f12_conj(f1, r);
+    f12_inv(e, f2, r, y0, y1, y2);
+    f12_mul(e, r, f1, f2);                 // f^(p^6-1)
+    f12_copy(f2, r);
+    f12_frobenius(e, r, r, 2);
+    f12_mul(e, r, r, f2);                  // ^(p^2+1)
+    f12_mul(e, y0, r, r);                  // y0 = r^2
+    f12_exp_by_x(e, y1, r);
+    f12_conj(y2, r);
+    f12_mul(e, y1, y1, y2);
+    f12_exp_by_x(e, y2, y1);
+    f12_conj(y1, y1);
+    f12_mul(e, y1, y1, y2);
+    f12_exp_by_x(e, y2, y1);
+    f12_frobenius(e, y1, y1, 1);
+    f12_mul(e, y1, y1, y2);
+    f12_mul(e, r, r, y0);
+    f12_exp_by_x(e, y0, y1);
+    f12_exp_by_x(e, y2, y0);
+    f12_frobenius(e, y0, y1, 2);
+    f12_conj(y1, y1);
+    f12_mul(e, y1, y1, y2);
+    f12_mul(e, y1, y1, y0);
+    f12_mul(e, r, r, y1);
+}
+
+// ---- Miller loop --------------------------------------------------------------------------------
+struct MillerState {
+    Fp rx[2], ry[2], rz[2];     // running G2 point, homogeneous projective
+    Fp qx[2], qy[2];            // Q affine
+    Fp px, py;                  // P affine
+    Fp co[3][2];                // line coefficients of the current step
+    F12 line;                   // sparse line value as a full Fp12 (zeros elsewhere)
+};
+
+__device__ __forceinline__ void fp2s_add(Fp *d, const Fp *a, const Fp *b) { Fp x = fp_add(a[0], b[0]), y = fp_add(a[1], b[1]); d[0] = x; d[1] = y; }
+__device__ __forceinline__ void fp2s_sub(Fp *d, const Fp *a, const Fp *b) { Fp x = fp_sub(a[0], b[0]), y = fp_sub(a[1], b[1]); d[0] = x; d[1] = y; }
+__device__ __forceinline__ void fp2s_neg(Fp *d, const Fp *a) { Fp x = fp_neg(a[0]), y = fp_neg(a[1]); d[0] = x; d[1] = y; }
+__device__ __forceinline__ void fp2s_half(Fp *d, const Fp *a, const Fp &two_inv) { Fp x = fp_mul(a[0], two_inv), y = fp_mul(a[1], two_inv); d[0] = x; d[1] = y; }
+
+// Doubling step (ark G2Prepared double_in_place), two product waves.
+__device__ void miller_double(Engine &e, MillerState &m) {
+    int tid = threadIdx.x;
+    Fp *T = e.tmp;     // T[0..1] = ry+rz
+    if (tid == 0) fp2s_add(&T[0], m.ry, m.rz);
+    __syncthreads();
+    // wave 1: 0: rx*ry  1: ry^2  2: rz^2  3: rx^2  4: (ry+rz)^2
+    if (tid < 15) {
+        int job = tid / 3, part = tid - job * 3;
+        const Fp *A, *B;
+        switch (job) {
+            case 0: A = m.rx; B = m.ry; break;
+            case 1: A = m.ry; B = m.ry; break;
+            case 2: A = m.rz; B = m.rz; break;
+            case 3: A = m.rx; B = m.rx; break;
+            default: A = &T[0]; B = &T[0]; break;
+        }
+        e.prod[tid] = fp2_part(part, A, B);
+    }
+    __syncthreads();
+    // linear stage: a, b, c, j, s -> e, f, g, h, i ; T layout: 2:a 4:b 6:e 8:g 10:h 12:(b-f)
+    if (tid == 0) {
+        Fp two_inv;
+#pragma unroll
+        for (int t = 0; t < 12; t++) two_inv.l[t] = DGC_TWO_INV[t];
+        Fp a[2], b[2], c[2], j[2], s[2], ee[2], f[2], g[2], h[2], i[2], t3[2];
+        fp2_from_parts(a, &e.prod[0]); fp2_from_parts(b, &e.prod[3]); fp2_from_parts(c, &e.prod[6]);
+        fp2_from_parts(j, &e.prod[9]); fp2_from_parts(s, &e.prod[12]);
+        fp2s_half(a, a, two_inv);
+        fp2s_add(t3, c, c); fp2s_add(t3, t3, c);                 // 3c
+        // e = (4+4u) * 3c = 4 * xi * 3c
+        Fp x0 = fp_sub(t3[0], t3[1]), x1 = fp_add(t3[0], t3[1]);
+        ee[0] = fp_dbl(fp_dbl(x0)); ee[1] = fp_dbl(fp_dbl(x1));
+        fp2s_add(f, ee, ee); fp2s_add(f, f, ee);                 // 3e
+        fp2s_add(g, b, f); fp2s_half(g, g, two_inv);
+        fp2s_add(t3, b, c); fp2s_sub(h, s, t3);
+        fp2s_sub(i, ee, b);
+        m.co[0][0] = i[0]; m.co[0][1] = i[1];
+        fp2s_add(t3, j, j); fp2s_add(t3, t3, j);
+        m.co[1][0] = t3[0]; m.co[1][1] = t3[1];
+        fp2s_neg(t3, h);
+        m.co[2][0] = t3[0]; m.co[2][1] = t3[1];
+        T[2] = a[0]; T[3] = a[1]; T[4] = b[0]; T[5] = b[1]; T[6] = ee[0]; T[7] = ee[1];
+        T[8] = g[0]; T[9] = g[1]; T[10] = h[0]; T[11] = h[1];
+        fp2s_sub(t3, b, f);
+        T[12] = t3[0]; T[13] = t3[1];
+    }
+    __syncthreads();
+    // wave 2: 0: a*(b-f)  1: g^2  2: e^2  3: b*h
+    if (tid < 12) {
+        int job = tid / 3, part = tid - job * 3;
+        const Fp *A, *B;
+        switch (job) {
+            case 0: A = &T[2]; B = &T[12]; break;
+            case 1: A = &T[8]; B = &T[8]; break;
+            case 2: A = &T[6]; B = &T[6]; break;
+            default: A = &T[4]; B = &T[10]; break;
+        }
+        e.prod[tid] = fp2_part(part, A, B);
+    }
+    __syncthreads();
+    if (tid == 0) {
+        Fp g2[2], e2[2], t3[2];
+        fp2_from_parts(m.rx, &e.prod[0]);
+        fp2_from_parts(g2, &e.prod[3]); fp2_from_parts(e2, &e.prod[6]);
+        fp2_from_parts(m.rz, &e.prod[9]);
+        fp2s_add(t3, e2, e2); fp2s_add(t3, t3, e2);
+        fp2s_sub(m.ry, g2, t3);
+    }
+    __syncthreads();
+}
+
+// Addition step (ark G2Prepared add_in_place), three product waves.
+__device__ void miller_add(Engine &e, MillerState &m) {
+    int tid = threadIdx.x;
+    Fp *T = e.tmp;   // 0: theta 2: lambda 4: c 6: d 8: e 10: f 12: g 14: h / (g-h)
+    // wave 1: qy*rz, qx*rz
+    if (tid < 6) {
+        int job = tid / 3, part = tid - job * 3;
+        e.prod[tid] = fp2_part(part, job == 0 ? m.qy : m.qx, m.rz);
+    }
+    __syncthreads();
+    if (tid == 0) {
+        Fp t[2];
+        fp2_from_parts(t, &e.prod[0]); fp2s_sub(&T[0], m.ry, t);      // theta
+        fp2_from_parts(t, &e.prod[3]); fp2s_sub(&T[2], m.rx, t);      // lambda
+    }
+    __syncthreads();
+    // wave 2: c = theta^2, d = lambda^2, theta*qx, lambda*qy
+    if (tid < 12) {
+        int job = tid / 3, part = tid - job * 3;
+        const Fp *A, *B;
+        switch (job) {
+            case 0: A = &T[0]; B = &T[0]; break;
+            case 1: A = &T[2]; B = &T[2]; break;
+            case 2: A = &T[0]; B = m.qx; break;
+            default: A = &T[2]; B = m.qy; break;
+        }
+        e.prod[tid] = fp2_part(part, A, B);
+    }
+    __syncthreads();
+    if (tid == 0) {
+        Fp a[2], b[2], t[2];
+        fp2_from_parts(&T[4], &e.prod[0]);        // c
+        fp2_from_parts(&T[6], &e.prod[3]);        // d
+        fp2_from_parts(a, &e.prod[6]); fp2_from_parts(b, &e.prod[9]);
+        fp2s_sub(t, a, b);                        // j
+        m.co[0][0] = t[0]; m.co[0][1] = t[1];
+        fp2s_neg(t, &T[0]);
+        m.co[1][0] = t[0]; m.co[1][1] = t[1];
+        m.co[2][0] = T[2]; m.co[2][1] = T[3];
+    }
+    __syncthreads();
+    // wave 3: e = lambda*d, f = rz*c, g = rx*d
+    if (tid < 9) {
+        int job = tid / 3, part = tid - job * 3;
+        const Fp *A, *B;
+        switch (job) {
+            case 0: A = &T[2]; B = &T[6]; break;
+            case 1: A = m.rz; B = &T[4]; break;
+            default: A = m.rx; B = &T[6]; break;
+        }
+        e.prod[tid] = fp2_part(part, A, B);
+    }
+    __syncthreads();
+    if (tid == 0) {
+        Fp t[2];
+        fp2_from_parts(&T[8], &e.prod[0]); fp2_from_parts(&T[10], &e.prod[3]); fp2_from_parts(&T[12], &e.prod[6]);
+        fp2s_add(t, &T[8], &T[10]); fp2s_sub(t, t, &T[12]); fp2s_sub(&T[14], t, &T[12]);   // h = e + f - 2g
+    }
+    __syncthreads();
+    // wave 4: lambda*h, theta*(g-h), e*ry, rz*e
+    if (tid == 0) { Fp t[2]; fp2s_sub(t, &T[12], &T[14]); T[12] = t[0]; T[13] = t[1]; }
+    __syncthreads();
+    if (tid < 12) {
+        int job = tid / 3, part = tid - job * 3;
+        const Fp *A, *B;
+        switch (job) {
+            case 0: A = &T[2]; B = &T[14]; break;
+            case 1: A = &T[0]; B = &T[12]; break;
+            case 2: A = &T[8]; B = m.ry; break;
+            default: A = m.rz; B = &T[8]; break;
+        }
+        e.prod[tid] = fp2_part(part, A, B);
+    }
+    __syncthreads();
+    if (tid == 0) {
+        Fp a[2], b[2];
+        fp2_from_parts(m.rx, &e.prod[0]);
+        fp2_from_parts(a, &e.prod[3]); fp2_from_parts(b, &e.prod[6]);
+        fp2s_sub(m.ry, a, b);
+        fp2_from_parts(m.rz, &e.prod[9]);
+    }
+    __syncthreads();
+}
+
+// f *= ell(coeffs, P): line = c0 + (c1*px) v + (c2*py) v w  -> positions w^0, w^2, w^3
+__device__ void miller_ell(Engine &e, MillerState &m, F12 *f) {
+    int tid = threadIdx.x;
+    if (tid < 12) m.line.c[tid] = fp_zero();
+    __syncthreads();
+    if (tid < 2) m.line.c[widx(0) + tid] = m.co[0][tid];
+    else if (tid < 4) m.line.c[widx(2) + (tid - 2)] = fp_mul(m.co[1][tid - 2], m.px);
+    else if (tid < 6) m.line.c[widx(3) + (tid - 4)] = fp_mul(m.co[2][tid - 4], m.py);
+    __syncthreads();
+    f12_mul(e, f, f, &m.line);
+}
+
+struct PairSmem {
+    Engine e;
+    MillerState m;
+    F12 f, t[5];
+};
+
+// One CTA per pair: out[pair] = Miller value (before the final conjugation), 1 for identity pairs.
+__global__ void __launch_bounds__(PAIR_THREADS) k_miller(const Affine<Fp> *g1, const Affine<Fp2> *g2, uint32_t k, F12 *out) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    PairSmem &S = *reinterpret_cast<PairSmem *>(smem_raw);
+    int tid = threadIdx.x;
+    uint32_t pair = blockIdx.x;
+    __shared__ int skip;
+    if (tid == 0) {
+        Affine<Fp> p = aff_load<Fp>(&g1[pair]);
+        Affine<Fp2> q = aff_load<Fp2>(&g2[pair]);
+        skip = aff_is_inf(p) || aff_is_inf(q);
+        S.m.px = p.x; S.m.py = p.y;
+        S.m.qx[0] = q.x.c0; S.m.qx[1] = q.x.c1; S.m.qy[0] = q.y.c0; S.m.qy[1] = q.y.c1;
+        S.m.rx[0] = q.x.c0; S.m.rx[1] = q.x.c1; S.m.ry[0] = q.y.c0; S.m.ry[1] = q.y.c1;
+        S.m.rz[0] = fp_one(); S.m.rz[1] = fp_zero();
+    }
+    f12_set_one(&S.f);
+    if (!skip) {
+        for (int i = 62; i >= 0; i--) {
+            f12_mul(S.e, &S.f, &S.f, &S.f);
+            miller_double(S.e, S.m);
+            miller_ell(S.e, S.m, &S.f);
+            if ((BLS_X_ABS >> i) & 1) {
+                miller_add(S.e, S.m);
+                miller_ell(S.e, S.m, &S.f);
+            }
+        }
+    }
+    if (tid < 12) fp_store(&out[pair].c[tid], S.f.c[tid]);
+}
+
+// out[b] = product of in[b*8 .. b*8+8)
+__global__ void __launch_bounds__(PAIR_THREADS) k_f12_reduce8(const F12 *in, uint32_t n, F12 *out) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    PairSmem &S = *reinterpret_cast<PairSmem *>(smem_raw);
+    int tid = threadIdx.x;
+    uint32_t lo = blockIdx.x * 8, hi = lo + 8 < n ? lo + 8 : n;
+    if (tid < 12) S.f.c[tid] = fp_load_rw(&in[lo].c[tid]);
+    __syncthreads();
+    for (uint32_t i = lo + 1; i < hi; i++) {
+        if (tid < 12) S.t[0].c[tid] = fp_load_rw(&in[i].c[tid]);
+        __syncthreads();
+        f12_mul(S.e, &S.f, &S.f, &S.t[0]);
+    }
+    if (tid < 12) fp_store(&out[blockIdx.x].c[tid], S.f.c[tid]);
+}
+
+// mode bit 0: conjugate first (Miller loop epilogue, x < 0); bit 1: final exponentiation;
+// in == nullptr means "one".  flags[0] = 1 iff the input to the final exponentiation was zero,
+// flags[1] = 1 iff the result equals one.
+__global__ void __launch_bounds__(PAIR_THREADS) k_f12_finish(const F12 *in, int mode, F12 *out, int32_t *flags) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    PairSmem &S = *reinterpret_cast<PairSmem *>(smem_raw);
+    int tid = threadIdx.x;
+    __shared__ int is_zero;
+    if (in) { if (tid < 12) S.f.c[tid] = fp_load_rw(&in->c[tid]); __syncthreads(); }
+    else f12_set_one(&S.f);
+    if (mode & 1) f12_conj(&S.f, &S.f);
+    if (tid == 0) {
+        int z = 1;
+        for (int i = 0; i < 12; i++) z &= fp_is_zero(S.f.c[i]);
+        is_zero = z;
+    }
+    __syncthreads();
+    if ((mode & 2) && !is_zero) f12_final_exp(S.e, &S.f, &S.t[0], &S.t[1], &S.t[2], &S.t[3], &S.t[4]);
+    if (tid < 12) fp_store(&out->c[tid], S.f.c[tid]);
+    if (tid == 0 && flags) {
+        flags[0] = (mode & 2) ? is_zero : 0;
+        int one = fp_eq(S.f.c[0], fp_one());
+        for (int i = 1; i < 12; i++) one &= fp_is_zero(S.f.c[i]);
+        flags[1] = one;
+    }
+}
+
+// out = a * b   /   out = a^scalar (255-bit canonical integer, MSB first square-and-multiply)
+__global__ void __launch_bounds__(PAIR_THREADS) k_f12_mul_or_pow(const F12 *a, const F12 *b, const uint32_t *scalar, F12 *out) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    PairSmem &S = *reinterpret_cast<PairSmem *>(smem_raw);
+    int tid = threadIdx.x;
+    if (tid < 12) S.t[0].c[tid] = fp_load_rw(&a->c[tid]);
+    __syncthreads();
+    if (b) {
+        if (tid < 12) S.t[1].c[tid] = fp_load_rw(&b->c[tid]);
+        __syncthreads();
+        f12_mul(S.e, &S.f, &S.t[0], &S.t[1]);
+    } else {
+        f12_set_one(&S.f);
+        for (int i = 255; i >= 0; i--) {
+            f12_mul(S.e, &S.f, &S.f, &S.f);
+            if ((scalar[i >> 5] >> (i & 31)) & 1) f12_mul(S.e, &S.f, &S.f, &S.t[0]);
+        }
+    }
+    if (tid < 12) fp_store(&out->c[tid], S.f.c[tid]);
+}
+
+static int32_t pairing_smem_opt_in() {
+    static bool done = false;
+    if (done) return DG_OK;
+    DG_CUDA(cudaFuncSetAttribute(k_miller, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PairSmem)));
+    DG_CUDA(cudaFuncSetAttribute(k_f12_reduce8, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PairSmem)));
+    DG_CUDA(cudaFuncSetAttribute(k_f12_finish, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PairSmem)));
+    DG_CUDA(cudaFuncSetAttribute(k_f12_mul_or_pow, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PairSmem)));
+    done = true;
+    return DG_OK;
+}
+
+// mode: 1 = Miller loop only (conjugated), 3 = Miller + final exponentiation
+static int32_t pairing_run(const uint8_t *g1, const uint8_t *g2, size_t k, int mode, uint8_t *out_fp12, int32_t *flags_out) {
+    int32_t rc = check_init();
+    if (rc) return rc;
+    if ((k && (!g1 || !g2)) || (!out_fp12 && !flags_out)) return fail(DG_ERR_BAD_ARG, "pairing: null pointer");
+    rc = pairing_smem_opt_in();
+    if (rc) return rc;
+    ThreadState &t = tls();
+    size_t need = Arena::pad(96 * k) + Arena::pad(192 * k) + 2 * Arena::pad(sizeof(F12) * (k + 1)) + Arena::pad(sizeof(F12)) + 256;
+    rc = t.arena.ensure(need, t.stream);
+    if (rc) return rc;
+    Affine<Fp> *d_p = t.arena.alloc<Affine<Fp>>(k ? k : 1);
+    Affine<Fp2> *d_q = t.arena.alloc<Affine<Fp2>>(k ? k : 1);
+    F12 *buf0 = t.arena.alloc<F12>(k + 1), *buf1 = t.arena.alloc<F12>(k + 1), *d_out = t.arena.alloc<F12>(1);
+    int32_t *d_flags = t.arena.alloc<int32_t>(2);
+    const F12 *cur = nullptr;
+    if (k) {
+        DG_CUDA(cudaMemcpyAsync(d_p, g1, 96 * k, cudaMemcpyHostToDevice, t.stream));
+        DG_CUDA(cudaMemcpyAsync(d_q, g2, 192 * k, cudaMemcpyHostToDevice, t.stream));
+        DG_LAUNCH(k_miller, (unsigned)k, PAIR_THREADS, sizeof(PairSmem), t.stream, d_p, d_q, (uint32_t)k, buf0);
+        size_t n = k;
+        F12 *src = buf0, *dst = buf1;
+        while (n > 1) {
+            unsigned nb = div_up(n, 8);
+            DG_LAUNCH(k_f12_reduce8, nb, PAIR_THREADS, sizeof(PairSmem), t.stream, src, (uint32_t)n, dst);
+            F12 *tmp = src; src = dst; dst = tmp;
+            n = nb;
+        }
+        cur = src;
+    }
+    DG_LAUNCH(k_f12_finish, 1, PAIR_THREADS, sizeof(PairSmem), t.stream, cur, mode, d_out, d_flags);
+    int32_t flags[2] = {0, 0};
+    if (out_fp12) DG_CUDA(cudaMemcpyAsync(out_fp12, d_out, sizeof(F12), cudaMemcpyDeviceToHost, t.stream));
+    DG_CUDA(cudaMemcpyAsync(t.err_flag_host + 8, d_flags, 8, cudaMemcpyDeviceToHost, t.stream));
+    DG_CUDA(cudaStreamSynchronize(t.stream));
+    flags[0] = ((int32_t *)(t.err_flag_host + 8))[0];
+    flags[1] = ((int32_t *)(t.err_flag_host + 8))[1];
+    if (flags_out) { flags_out[0] = flags[0]; flags_out[1] = flags[1]; }
+    return DG_OK;
+}
+
+}  // namespace dg
+
+using namespace dg;
+
+extern "C" {
+
+int32_t dg_multi_miller_loop(const uint8_t *g1, const uint8_t *g2, size_t k, uint8_t *out_fp12) {
+    if (!out_fp12) return fail(DG_ERR_BAD_ARG, "multi_miller_loop: null output");
+    return pairing_run(g1, g2, k, 1, out_fp12, nullptr);
+}
+int32_t dg_multi_pairing(const uint8_t *g1, const uint8_t *g2, size_t k, uint8_t *out_fp12) {
+    if (!out_fp12) return fail(DG_ERR_BAD_ARG, "multi_pairing: null output");
+    return pairing_run(g1, g2, k, 3, out_fp12, nullptr);
+}
+int32_t dg_multi_pairing_is_one(const uint8_t *g1, const uint8_t *g2, size_t k, int32_t *result) {
+    if (!result) return fail(DG_ERR_BAD_ARG, "multi_pairing_is_one: null output");
+    int32_t flags[2];
+    int32_t rc = pairing_run(g1, g2, k, 3, nullptr, flags);
+    if (rc) return rc;
+    *result = flags[1];
+    return DG_OK;
+}
+
+int32_t dg_final_exponentiation(const uint8_t *in_fp12, uint8_t *out_fp12, int32_t *is_some) {
+    int32_t rc = check_init();
+    if (rc) return rc;
+    if (!in_fp12 || !out_fp12 || !is_some) return fail(DG_ERR_BAD_ARG, "final_exponentiation: null pointer");
+    rc = pairing_smem_opt_in();
+    if (rc) return rc;
+    ThreadState &t = tls();
+    rc = t.arena.ensure(2 * Arena::pad(sizeof(F12)) + 256, t.stream);
+    if (rc) return rc;
+    F12 *d_in = t.arena.alloc<F12>(1), *d_out = t.arena.alloc<F12>(1);
+    int32_t *d_flags = t.arena.alloc<int32_t>(2);
+    DG_CUDA(cudaMemcpyAsync(d_in, in_fp12, sizeof(F12), cudaMemcpyHostToDevice, t.stream));
+    DG_LAUNCH(k_f12_finish, 1, PAIR_THREADS, sizeof(PairSmem), t.stream, d_in, 2, d_out, d_flags);
+    DG_CUDA(cudaMemcpyAsync(out_fp12, d_out, sizeof(F12), cudaMemcpyDeviceToHost, t.stream));
+    DG_CUDA(cudaMemcpyAsync(t.err_flag_host + 8, d_flags, 8, cudaMemcpyDeviceToHost, t.stream));
+    DG_CUDA(cudaStreamSynchronize(t.stream));
+    *is_some = ((int32_t *)(t.err_flag_host + 8))[0] ? 0 : 1;
+    return DG_OK;
+}
+
+static int32_t f12_binary(const uint8_t *a, const uint8_t *b, const uint8_t *scalar, uint8_t *out) {
+    int32_t rc = check_init();
+    if (rc) return rc;
+    if (!a || !out || (!b && !scalar)) return fail(DG_ERR_BAD_ARG, "fp12 op: null pointer");
+    rc = pairing_smem_opt_in();
+    if (rc) return rc;
+    ThreadState &t = tls();
+    rc = t.arena.ensure(3 * Arena::pad(sizeof(F12)) + 256, t.stream);
+    if (rc) return rc;
+    F12 *d_a = t.arena.alloc<F12>(1), *d_b = t.arena.alloc<F12>(1), *d_out = t.arena.alloc<F12>(1);
+    uint32_t *d_s = t.arena.alloc<uint32_t>(8);
+    DG_CUDA(cudaMemcpyAsync(d_a, a, sizeof(F12), cudaMemcpyHostToDevice, t.stream));
+    if (b) DG_CUDA(cudaMemcpyAsync(d_b, b, sizeof(F12), cudaMemcpyHostToDevice, t.stream));
+    else DG_CUDA(cudaMemcpyAsync(d_s, scalar, 32, cudaMemcpyHostToDevice, t.stream));
+    DG_LAUNCH(k_f12_mul_or_pow, 1, PAIR_THREADS, sizeof(PairSmem), t.stream, d_a, b ? d_b : (const F12 *)nullptr, d_s, d_out);
+    DG_CUDA(cudaMemcpyAsync(out, d_out, sizeof(F12), cudaMemcpyDeviceToHost, t.stream));
+    DG_CUDA(cudaStreamSynchronize(t.stream));
+    return DG_OK;
+}
+int32_t dg_gt_pow(const uint8_t *in_fp12, const uint8_t *scalar, uint8_t *out_fp12) { return f12_binary(in_fp12, nullptr, scalar, out_fp12); }
+int32_t dg_fp12_mul(const uint8_t *a, const uint8_t *b, uint8_t *out) { return f12_binary(a, b, nullptr, out); }
+
+}  // extern "C"

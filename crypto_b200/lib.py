@@ -1,0 +1,286 @@
+"""ctypes binding of libdockgpu.so (include/dockgpu.h).
+
+There is NO CPU fallback: if the CUDA library is missing or no B200 is visible, every entry
+point raises.  The oracle under oracle/ is never imported from here.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, 'libdockgpu.so')
+
+G1_AFF, G1_JAC, G2_AFF, G2_JAC, FP12, SCALAR = 96, 144, 192, 288, 576, 32
+
+# every symbol include/dockgpu.h declares (checked by tests/test_abi.py without a GPU)
+EXPORTS = [
+    'dg_init', 'dg_shutdown', 'dg_last_error', 'dg_launch_count', 'dg_sync',
+    'dg_bases_upload_g1', 'dg_bases_upload_g2', 'dg_bases_free',
+    'dg_msm_g1', 'dg_msm_g2', 'dg_msm_g1_device', 'dg_msm_g2_device', 'dg_msm_set_window',
+    'dg_fixed_base_table_g1', 'dg_fixed_base_table_g2', 'dg_fixed_base_table_info',
+    'dg_fixed_base_table_download', 'dg_fixed_base_table_free',
+    'dg_fixed_base_mul_many_g1', 'dg_fixed_base_mul_many_g2',
+    'dg_batch_mul_g1', 'dg_batch_mul_g2', 'dg_batch_mul_add_fixed_g1',
+    'dg_normalize_batch_g1', 'dg_normalize_batch_g2',
+    'dg_multi_miller_loop', 'dg_final_exponentiation', 'dg_multi_pairing', 'dg_multi_pairing_is_one',
+    'dg_gt_pow', 'dg_fp12_mul',
+    'dg_fold_g1', 'dg_fold_g1_device', 'dg_fold_g2',
+    'dg_dbg_fp_op',
+]
+
+
+class DockGpuError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__('libdockgpu error %d: %s' % (code, msg))
+        self.code = code
+
+
+_lib = None
+_inited = False
+
+
+def load():
+    """dlopen the library without touching the GPU."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise DockGpuError(-4, 'libdockgpu.so is not built (run `python -m crypto_b200.build`); '
+                                   'there is no CPU fallback')
+        _lib = C.CDLL(LIB_PATH)
+        _lib.dg_launch_count.restype = C.c_uint64
+        for name in EXPORTS:
+            if name != 'dg_launch_count' and hasattr(_lib, name):
+                getattr(_lib, name).restype = C.c_int32
+    return _lib
+
+
+def _check(rc):
+    if rc != 0:
+        buf = C.create_string_buffer(512)
+        _lib.dg_last_error(buf, C.c_size_t(512))
+        raise DockGpuError(rc, buf.value.decode(errors='replace'))
+
+
+def init(device=-1):
+    global _inited
+    lib = load()
+    if not _inited:
+        _check(lib.dg_init(C.c_int32(device)))
+        _inited = True
+    return lib
+
+
+def launch_count():
+    return int(load().dg_launch_count())
+
+
+def sync():
+    _check(init().dg_sync())
+
+
+def _in(a, rec=None):
+    """Contiguous uint8 view of bytes / ndarray input; returns (keepalive, void*)."""
+    if isinstance(a, (bytes, bytearray, memoryview)):
+        a = np.frombuffer(a, dtype=np.uint8)
+    a = np.ascontiguousarray(a).view(np.uint8).reshape(-1)
+    return a, C.c_void_p(a.ctypes.data)
+
+
+def _out(nbytes):
+    a = np.zeros(max(nbytes, 1), dtype=np.uint8)
+    return a, C.c_void_p(a.ctypes.data)
+
+
+# ---- resident bases -----------------------------------------------------------------------------
+class Bases:
+    """Device-resident affine bases (proving-key model)."""
+
+    def __init__(self, affine, g2=False):
+        lib = init()
+        a, ap = _in(affine)
+        self.g2 = g2
+        self.n = a.size // (G2_AFF if g2 else G1_AFF)
+        h = C.c_uint64(0)
+        fn = lib.dg_bases_upload_g2 if g2 else lib.dg_bases_upload_g1
+        _check(fn(ap, C.c_size_t(self.n), C.byref(h)))
+        self.handle = h.value
+
+    def free(self):
+        if self.handle:
+            _check(load().dg_bases_free(C.c_uint64(self.handle)))
+            self.handle = 0
+
+
+def msm(bases, scalars, g2=False, n=None):
+    """sum s_i * P_i -> Jacobian record (144 / 288 B).  `bases` is a Bases handle or affine
+    records; inputs are truncated to the shorter one like ark's msm_bigint."""
+    lib = init()
+    s, sp = _in(scalars)
+    ns = s.size // SCALAR
+    fn = lib.dg_msm_g2 if g2 else lib.dg_msm_g1
+    o, op = _out(G2_JAC if g2 else G1_JAC)
+    if isinstance(bases, Bases):
+        assert bases.g2 == g2
+        k = min(ns, bases.n) if n is None else n
+        _check(fn(C.c_uint64(bases.handle), None, sp, C.c_size_t(k), op))
+    else:
+        b, bp = _in(bases)
+        k = min(ns, b.size // (G2_AFF if g2 else G1_AFF)) if n is None else n
+        _check(fn(C.c_uint64(0), bp if k else None, sp, C.c_size_t(k), op))
+    return o[:G2_JAC if g2 else G1_JAC]
+
+
+def msm_device(bases_ptr, scalars_ptr, n, out_ptr, stream=0, g2=False):
+    """Device-pointer variant (no copies, no sync)."""
+    lib = init()
+    fn = lib.dg_msm_g2_device if g2 else lib.dg_msm_g1_device
+    _check(fn(C.c_void_p(bases_ptr), C.c_void_p(scalars_ptr), C.c_size_t(n), C.c_void_p(out_ptr), C.c_void_p(stream)))
+
+
+def msm_set_window(c):
+    _check(init().dg_msm_set_window(C.c_int32(c)))
+
+
+# ---- fixed base ---------------------------------------------------------------------------------
+class FixedBaseTable:
+    def __init__(self, point_affine, hint_n, g2=False):
+        lib = init()
+        p, pp = _in(point_affine)
+        self.g2 = g2
+        h = C.c_uint64(0)
+        fn = lib.dg_fixed_base_table_g2 if g2 else lib.dg_fixed_base_table_g1
+        _check(fn(pp, C.c_size_t(hint_n), C.byref(h)))
+        self.handle = h.value
+        w, nw, is2 = C.c_int32(0), C.c_int32(0), C.c_int32(0)
+        _check(lib.dg_fixed_base_table_info(C.c_uint64(self.handle), C.byref(w), C.byref(nw), C.byref(is2)))
+        self.window, self.num_windows = w.value, nw.value
+
+    def download(self):
+        rec = G2_AFF if self.g2 else G1_AFF
+        o, op = _out(rec * (self.num_windows << self.window))
+        _check(load().dg_fixed_base_table_download(C.c_uint64(self.handle), op))
+        return o
+
+    def mul_many(self, scalars):
+        lib = load()
+        s, sp = _in(scalars)
+        m = s.size // SCALAR
+        rec = G2_JAC if self.g2 else G1_JAC
+        o, op = _out(rec * m)
+        fn = lib.dg_fixed_base_mul_many_g2 if self.g2 else lib.dg_fixed_base_mul_many_g1
+        _check(fn(C.c_uint64(self.handle), sp, C.c_size_t(m), op))
+        return o[:rec * m]
+
+    def free(self):
+        if self.handle:
+            _check(load().dg_fixed_base_table_free(C.c_uint64(self.handle)))
+            self.handle = 0
+
+
+def batch_mul(points, scalars, g2=False):
+    lib = init()
+    p, pp = _in(points); s, sp = _in(scalars)
+    m = min(s.size // SCALAR, p.size // (G2_AFF if g2 else G1_AFF))
+    rec = G2_JAC if g2 else G1_JAC
+    o, op = _out(rec * m)
+    fn = lib.dg_batch_mul_g2 if g2 else lib.dg_batch_mul_g1
+    _check(fn(pp, sp, C.c_size_t(m), op))
+    return o[:rec * m]
+
+
+def batch_mul_add_fixed_g1(points, scalars_a, table, scalars_b):
+    lib = init()
+    p, pp = _in(points); a, ap = _in(scalars_a); b, bp = _in(scalars_b)
+    m = a.size // SCALAR
+    o, op = _out(G1_AFF * m)
+    _check(lib.dg_batch_mul_add_fixed_g1(pp, ap, C.c_uint64(table.handle), bp, C.c_size_t(m), op))
+    return o[:G1_AFF * m]
+
+
+def normalize_batch(jac, g2=False):
+    lib = init()
+    j, jp = _in(jac)
+    m = j.size // (G2_JAC if g2 else G1_JAC)
+    rec = G2_AFF if g2 else G1_AFF
+    o, op = _out(rec * m)
+    fn = lib.dg_normalize_batch_g2 if g2 else lib.dg_normalize_batch_g1
+    _check(fn(jp, C.c_size_t(m), op))
+    return o[:rec * m]
+
+
+def fold(jac_points, g2=False):
+    lib = init()
+    j, jp = _in(jac_points)
+    rec = G2_JAC if g2 else G1_JAC
+    k = j.size // rec
+    o, op = _out(rec)
+    fn = lib.dg_fold_g2 if g2 else lib.dg_fold_g1
+    _check(fn(jp, C.c_size_t(k), op))
+    return o[:rec]
+
+
+def fold_g1_device(jac_ptr, k, out_ptr, stream=0):
+    _check(init().dg_fold_g1_device(C.c_void_p(jac_ptr), C.c_size_t(k), C.c_void_p(out_ptr), C.c_void_p(stream)))
+
+
+# ---- pairing ------------------------------------------------------------------------------------
+def multi_miller_loop(g1s, g2s):
+    lib = init()
+    a, ap = _in(g1s); b, bp = _in(g2s)
+    k = min(a.size // G1_AFF, b.size // G2_AFF)
+    o, op = _out(FP12)
+    _check(lib.dg_multi_miller_loop(ap, bp, C.c_size_t(k), op))
+    return o[:FP12]
+
+
+def final_exponentiation(f):
+    lib = init()
+    a, ap = _in(f)
+    o, op = _out(FP12)
+    some = C.c_int32(0)
+    _check(lib.dg_final_exponentiation(ap, op, C.byref(some)))
+    return o[:FP12] if some.value else None
+
+
+def multi_pairing(g1s, g2s):
+    lib = init()
+    a, ap = _in(g1s); b, bp = _in(g2s)
+    k = min(a.size // G1_AFF, b.size // G2_AFF)
+    o, op = _out(FP12)
+    _check(lib.dg_multi_pairing(ap, bp, C.c_size_t(k), op))
+    return o[:FP12]
+
+
+def multi_pairing_is_one(g1s, g2s):
+    lib = init()
+    a, ap = _in(g1s); b, bp = _in(g2s)
+    k = min(a.size // G1_AFF, b.size // G2_AFF)
+    r = C.c_int32(0)
+    _check(lib.dg_multi_pairing_is_one(ap, bp, C.c_size_t(k), C.byref(r)))
+    return bool(r.value)
+
+
+def gt_pow(f, scalar):
+    lib = init()
+    a, ap = _in(f); s, sp = _in(scalar)
+    o, op = _out(FP12)
+    _check(lib.dg_gt_pow(ap, sp, op))
+    return o[:FP12]
+
+
+def fp12_mul(a, b):
+    lib = init()
+    x, xp = _in(a); y, yp = _in(b)
+    o, op = _out(FP12)
+    _check(lib.dg_fp12_mul(xp, yp, op))
+    return o[:FP12]
+
+
+def dbg_fp_op(op_code, a, b):
+    lib = init()
+    x, xp = _in(a); y, yp = _in(b)
+    n = x.size // 48
+    o, op = _out(48 * n)
+    _check(lib.dg_dbg_fp_op(C.c_int32(op_code), xp, yp, C.c_size_t(n), op))
+    return o[:48 * n]

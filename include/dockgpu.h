@@ -1,0 +1,147 @@
+/* dockgpu.h -- C ABI of the B200-native BLS12-381 MSM / fixed-base / multi-pairing backend.
+ *
+ * This is the drop-in boundary for docknetwork/crypto's hot path.  The
+ * reference has no FFI for this path today: it calls the arkworks traits directly.  Each entry
+ * point below names the reference call(s) a Rust binding would route to it; INTEGRATION.md shows
+ * the `extern "C"` block and the ark-ec patch that does the routing.
+ *
+ * Conventions
+ *  - Every function returns 0 (DG_OK) or a negative dg_status; no exceptions cross the boundary.
+ *    dg_last_error() gives a thread-local human-readable message.
+ *  - Caller owns all host memory; outputs go to caller-owned buffers.  The library owns device
+ *    memory behind opaque 64-bit handles.
+ *  - Field elements are little-endian Montgomery limbs exactly as ark-ff stores them
+ *    (Fp: 48 B, R = 2^384; Fp2: c0||c1).  Points cross as packed records:
+ *        G1 affine  96 B  x||y          G2 affine 192 B  x.c0||x.c1||y.c0||y.c1
+ *        G1 Jacobian 144 B x||y||z      G2 Jacobian 288 B        (ark Projective{x,y,z})
+ *        Fp12 576 B  c0.c0.c0 || c0.c0.c1 || c0.c1.c0 ... c1.c2.c1 (ark field order)
+ *    The point at infinity is the all-zero affine record (x = y = 0 is not on either curve);
+ *    Jacobian outputs use z = 0 (x = y = R, i.e. ark's Projective::zero()).
+ *  - Scalars are canonical (non-Montgomery) 256-bit little-endian integers < 2^255, i.e. the
+ *    BigInt<4> that `Fr::into_bigint()` yields and `msm_bigint` receives.
+ *  - Thread safety: calls may be issued concurrently from many host threads (rayon workers);
+ *    each call uses a per-thread stream and scratch arena.  dg_init is idempotent.
+ *  - *_device variants take device pointers and a cudaStream_t (as void*) and do not
+ *    synchronise; they exist so callers that already keep operands in HBM (proving keys,
+ *    chained operations, benchmarks) avoid staging copies.
+ */
+#ifndef DOCKGPU_H
+#define DOCKGPU_H
+#include <stddef.h>
+#include <stdint.h>
+
+#if defined(__GNUC__)
+#pragma GCC visibility push(default)
+#endif
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum {
+    DG_OK = 0,
+    DG_ERR_BAD_ARG = -1,     /* null pointer, bad handle, scalar >= 2^255 ... */
+    DG_ERR_CUDA = -2,        /* a CUDA runtime call failed (message in dg_last_error) */
+    DG_ERR_OOM = -3,         /* device allocation failed */
+    DG_ERR_NOT_INIT = -4
+} dg_status;
+
+/* ---- lifecycle -------------------------------------------------------------------------- */
+/* Select the CUDA device this process drives (one process per GPU) and create the context.
+ * device < 0 keeps the current device.  Idempotent. */
+int32_t dg_init(int32_t device);
+int32_t dg_shutdown(void);
+/* Copies the calling thread's last error message (NUL-terminated, truncated to cap). */
+int32_t dg_last_error(char *buf, size_t cap);
+/* Number of kernels this library has launched so far in this process (bench.py gpu_launches). */
+uint64_t dg_launch_count(void);
+/* Blocks until all work issued by the calling thread's stream has finished. */
+int32_t dg_sync(void);
+
+/* ---- resident bases (proving-key model: upload once, reuse across MSMs) -------------------
+ * Replaces nothing in the reference API; it is the device-side cache for
+ * legogroth16::ProvingKeyCommon vectors (legogroth16/src/data_structures.rs:151-168) and BBS+
+ * SignatureParamsG1::h (bbs_plus/src/setup.rs:128-146). */
+int32_t dg_bases_upload_g1(const uint8_t *affine, size_t n, uint64_t *handle);
+int32_t dg_bases_upload_g2(const uint8_t *affine, size_t n, uint64_t *handle);
+int32_t dg_bases_free(uint64_t handle);
+
+/* ---- variable-base MSM ---------------------------------------------------------------------
+ * ark_ec::VariableBaseMSM::msm_bigint(bases, bigints) for G1Projective / G2Projective
+ * (legogroth16/src/prover.rs:215,286,299,363,404,456,592; via msm_unchecked at
+ * bbs_plus/src/setup.rs:145,192, bbs_plus/src/proof.rs:580,
+ * schnorr_pok/src/pok_generalized_pedersen.rs:97,153, vb_accumulator/src/batch_utils.rs:667,
+ * vb_accumulator/src/witness.rs:415, utils/src/randomized_mult_checker.rs:100,
+ * utils/src/pairs.rs:146,154).  The caller truncates to min(len) as arkworks does.
+ * Exactly one of (bases_handle != 0, bases != NULL) selects the bases; with a handle, `n` may be
+ * smaller than the uploaded count (prefix).  out: one Jacobian point. */
+int32_t dg_msm_g1(uint64_t bases_handle, const uint8_t *bases, const uint8_t *scalars, size_t n, uint8_t *out_jac);
+int32_t dg_msm_g2(uint64_t bases_handle, const uint8_t *bases, const uint8_t *scalars, size_t n, uint8_t *out_jac);
+/* device-pointer variants; out_jac_dev is device memory (144 / 288 B) */
+int32_t dg_msm_g1_device(const void *bases_dev, const void *scalars_dev, size_t n, void *out_jac_dev, void *stream);
+int32_t dg_msm_g2_device(const void *bases_dev, const void *scalars_dev, size_t n, void *out_jac_dev, void *stream);
+/* Overrides the automatic window size (0 restores it); for tuning and tests. */
+int32_t dg_msm_set_window(int32_t c);
+
+/* ---- fixed-base batch multiplication --------------------------------------------------------
+ * utils::msm::WindowTable::new(num_multiplications, group_elem) (utils/src/msm.rs:18-30):
+ * window = FixedBase::get_mul_window_size(hint_n), table[k][j] = j * 2^(k*window) * g. */
+int32_t dg_fixed_base_table_g1(const uint8_t *point_affine, size_t hint_n, uint64_t *table_handle);
+int32_t dg_fixed_base_table_g2(const uint8_t *point_affine, size_t hint_n, uint64_t *table_handle);
+/* scalar_size / window_size / num_windows fields of WindowTable (utils/src/msm.rs:8-13) */
+int32_t dg_fixed_base_table_info(uint64_t table_handle, int32_t *window, int32_t *num_windows, int32_t *is_g2);
+/* Copies the affine table to the host, row-major num_windows x 2^window records (serialisation
+ * of WindowTable, utils/src/msm.rs:7). */
+int32_t dg_fixed_base_table_download(uint64_t table_handle, uint8_t *out_affine);
+int32_t dg_fixed_base_table_free(uint64_t table_handle);
+/* WindowTable::multiply_many / multiply_field_elems_with_same_group_elem (utils/src/msm.rs:38-62)
+ * = FixedBase::msm: out m Jacobian points. */
+int32_t dg_fixed_base_mul_many_g1(uint64_t table_handle, const uint8_t *scalars, size_t m, uint8_t *out_jac);
+int32_t dg_fixed_base_mul_many_g2(uint64_t table_handle, const uint8_t *scalars, size_t m, uint8_t *out_jac);
+
+/* ---- independent scalar multiplications ----------------------------------------------------
+ * AffineRepr::mul_bigint inside cfg_iter! maps (vb_accumulator/src/witness.rs:190,229,278;
+ * utils/src/randomized_pairing_check.rs:126,153,157): out[i] = [s_i] P_i, Jacobian. */
+int32_t dg_batch_mul_g1(const uint8_t *points_affine, const uint8_t *scalars, size_t m, uint8_t *out_jac);
+int32_t dg_batch_mul_g2(const uint8_t *points_affine, const uint8_t *scalars, size_t m, uint8_t *out_jac);
+/* Fused accumulator witness update (vb_accumulator/src/witness.rs:269-284):
+ * out[i] = normalize( [a_i] P_i + [b_i] V ), V given by its window table.  out: m affine. */
+int32_t dg_batch_mul_add_fixed_g1(const uint8_t *points_affine, const uint8_t *scalars_a, uint64_t table_handle,
+                                  const uint8_t *scalars_b, size_t m, uint8_t *out_affine);
+
+/* ---- CurveGroup::normalize_batch ------------------------------------------------------------
+ * (vb_accumulator/src/witness.rs:193,232,284; batch_utils.rs:506,524,633,651). */
+int32_t dg_normalize_batch_g1(const uint8_t *jac, size_t m, uint8_t *out_affine);
+int32_t dg_normalize_batch_g2(const uint8_t *jac, size_t m, uint8_t *out_affine);
+
+/* ---- pairing ---------------------------------------------------------------------------------
+ * ark_ec::pairing::Pairing for Bls12_381 (bbs_plus/src/proof.rs:494,
+ * legogroth16/src/verifier.rs:69-80, utils/src/randomized_pairing_check.rs:134,204-214):
+ * multi_miller_loop drops pairs with an identity on either side; final_exponentiation returns
+ * None (is_some = 0) iff the input is zero. */
+int32_t dg_multi_miller_loop(const uint8_t *g1_affine, const uint8_t *g2_affine, size_t k, uint8_t *out_fp12);
+int32_t dg_final_exponentiation(const uint8_t *in_fp12, uint8_t *out_fp12, int32_t *is_some);
+int32_t dg_multi_pairing(const uint8_t *g1_affine, const uint8_t *g2_affine, size_t k, uint8_t *out_fp12);
+/* result = 1 iff prod e(P_i, Q_i) == 1 */
+int32_t dg_multi_pairing_is_one(const uint8_t *g1_affine, const uint8_t *g2_affine, size_t k, int32_t *result);
+/* Target-group helpers used by RandomizedPairingChecker (right += out * m, left *= miller):
+ * PairingOutput::mul_bigint and Fp12 multiplication. */
+int32_t dg_gt_pow(const uint8_t *in_fp12, const uint8_t *scalar, uint8_t *out_fp12);
+int32_t dg_fp12_mul(const uint8_t *a_fp12, const uint8_t *b_fp12, uint8_t *out_fp12);
+
+/* ---- multi-GPU combine ------------------------------------------------------------------------
+ * Folds k Jacobian partial results (one per rank, gathered by the host's NCCL all-gather) into
+ * one: the "all-reduce under the group law" of SURVEY.md 8e. */
+int32_t dg_fold_g1(const uint8_t *jac_points, size_t k, uint8_t *out_jac);
+int32_t dg_fold_g1_device(const void *jac_points_dev, size_t k, void *out_jac_dev, void *stream);
+int32_t dg_fold_g2(const uint8_t *jac_points, size_t k, uint8_t *out_jac);
+
+/* ---- test hooks (field arithmetic parity; not part of the reference-facing surface) ---------- */
+int32_t dg_dbg_fp_op(int32_t op, const uint8_t *a, const uint8_t *b, size_t n, uint8_t *out);
+
+#ifdef __cplusplus
+}
+#endif
+#if defined(__GNUC__)
+#pragma GCC visibility pop
+#endif
+#endif /* DOCKGPU_H */

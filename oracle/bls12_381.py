@@ -303,7 +303,7 @@ def fixed_base_window_size(n):
     return 3 if n < 32 else ln_without_floats(n)
 
 def make_digits(s, c, num_bits=255):
-    """Signed radix-2^c digits, digit in (-2^(c-1), 2^(c-1)] (ark make_digits)."""
+    """Signed radix-2^c digits, digit in [-2^(c-1), 2^(c-1)), last one unsigned (ark make_digits)."""
     n = (num_bits + c - 1) // c
     radix, half = 1 << c, 1 << (c - 1)
     out, carry = [], 0
@@ -325,7 +325,7 @@ def msm_pippenger(curve, bases, scalars):
     digits = [make_digits(s, c) for s in scalars]
     window_sums = []
     for w in range(nd):
-        buckets = [None] * (1 << (c - 1))
+        buckets = [None] * (1 << c)    # ark allocates 1 << c: the top digit is left unsigned
         for i in range(n):
             d = digits[i][w]
             if d > 0:

@@ -146,7 +146,7 @@ static void PN(msm_bigint)(PN(jac) *out, const PN(aff) *bases, const uint64_t *s
     PN(jac) *wsum = (PN(jac) *)malloc(sizeof(PN(jac)) * nd);
 #pragma omp parallel for schedule(dynamic, 1)
     for (int w = 0; w < nd; w++) {
-        size_t nb = (size_t)1 << (c - 1);
+        size_t nb = (size_t)1 << c;   /* ark allocates 1 << c: the top digit is left unsigned */
         PN(jac) *buckets = (PN(jac) *)malloc(sizeof(PN(jac)) * nb);
         for (size_t b = 0; b < nb; b++) PN(jac_zero)(&buckets[b]);
         for (size_t i = 0; i < n; i++) {

@@ -1,0 +1,43 @@
+"""CPU: host-side mirror logic that needs no GPU (window rules, marshalling, checker bookkeeping)."""
+import numpy as np
+import pytest
+
+from crypto_b200 import msm
+from oracle import bls12_381 as o
+
+
+def test_window_size_rule_matches_ark():
+    for n in (1, 10, 31, 32, 33, 1000, 10000, 1 << 19):
+        assert msm.WindowTable.window_size_for(n) == o.fixed_base_window_size(n)
+
+
+def test_scalar_marshalling():
+    b = msm.scalars_to_bytes([0, 1, o.R - 1, o.R + 5])
+    assert b.size == 128
+    assert bytes(b[32:64]) == (1).to_bytes(32, 'little')
+    assert bytes(b[96:128]) == (5).to_bytes(32, 'little')       # reduced mod r like Fr
+    raw = np.arange(64, dtype=np.uint8)
+    assert msm.scalars_to_bytes(raw) is not None and msm.scalars_to_bytes(bytes(raw)).size == 64
+
+
+def test_mult_checker_dedups_by_x_coordinate():
+    """utils/src/randomized_mult_checker.rs:107-125: P and -P share one entry."""
+    p = o.E1.mul(o.G1_GEN, 5)
+    pb, nb = o.g1_to_bytes(p), o.g1_to_bytes(o.E1.neg(p))
+    ck = msm.RandomizedMultChecker(7)
+    ck._add(pb, 10)
+    ck._add(pb, 5)
+    ck._add(nb, 3)
+    ck._add(bytes(96), 99)           # identity ignored
+    assert len(ck) == 1
+    (scalar, point), = ck.args.values()
+    assert scalar == 12 and point == pb
+    ck.add_1(pb, 2, o.g1_to_bytes(o.E1.mul(p, 2)))
+    assert ck.current_random == 7
+
+
+def test_length_mismatch_error():
+    v = msm.VariableBaseMSM()
+    with pytest.raises(msm.LengthMismatch) as ei:
+        v.msm(bytes(96 * 3), [1, 2])
+    assert ei.value.min_len == 2
