@@ -102,6 +102,8 @@ __global__ void __launch_bounds__(128) k_fixed_rows(const Jac<F> *__restrict__ g
     uint32_t k = tid >> window, j = tid & (in_window - 1);
     Jac<F> base = jac_load<F>(&gouter[k]);
     XYZZ<F> b = jac_to_xyzz(base), acc = xyzz_inf<F>();
+    // ark's last row only has 2^(255 - (outerc-1)*window) entries; the rest stays the identity
+    if (k == (uint32_t)outerc - 1 && j >= (1u << (255 - (outerc - 1) * window))) j = 0;
     for (int bit = window - 1; bit >= 0; bit--) {
         if (!xyzz_is_inf(acc)) acc = xyzz_dbl(acc);
         if ((j >> bit) & 1) acc = xyzz_add(acc, b);

@@ -215,6 +215,27 @@ int32_t dg_msm_g1(uint64_t h, const uint8_t *bases, const uint8_t *scalars, size
 int32_t dg_msm_g2(uint64_t h, const uint8_t *bases, const uint8_t *scalars, size_t n, uint8_t *out) { return msm_host<true>(h, bases, scalars, n, out); }
 int32_t dg_msm_g1_device(const void *b, const void *s, size_t n, void *o, void *st) { return msm_device<false>(b, s, n, o, st); }
 int32_t dg_msm_g2_device(const void *b, const void *s, size_t n, void *o, void *st) { return msm_device<true>(b, s, n, o, st); }
+int32_t dg_prof_enable(int32_t on) {
+    ctx().prof_enabled.store(on ? 1 : 0);
+    return DG_OK;
+}
+int32_t dg_prof_read_accumulate(double *mean_ms, int32_t *count) {
+    if (!mean_ms || !count) return fail(DG_ERR_BAD_ARG, "prof_read: null pointer");
+    DG_CUDA(cudaDeviceSynchronize());
+    std::lock_guard<std::mutex> lk(ctx().mu);
+    double tot = 0;
+    int n = 0;
+    for (auto &pr : ctx().prof_events) {
+        float ms = 0;
+        if (cudaEventElapsedTime(&ms, pr.first, pr.second) == cudaSuccess) { tot += ms; n++; }
+        cudaEventDestroy(pr.first);
+        cudaEventDestroy(pr.second);
+    }
+    ctx().prof_events.clear();
+    *mean_ms = n ? tot / n : 0.0;
+    *count = n;
+    return DG_OK;
+}
 int32_t dg_msm_set_window(int32_t c) {
     if (c < 0 || c == 1 || c > 24) return fail(DG_ERR_BAD_ARG, "msm_set_window: c must be 0 or in [2, 24]");
     ctx().msm_window_override.store(c);

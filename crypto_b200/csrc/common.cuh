@@ -29,6 +29,10 @@ struct Context {
     uint64_t next_handle = 1;
     std::atomic<uint64_t> launches{0};
     std::atomic<int> msm_window_override{0};
+    // optional per-kernel timing of the dominant kernel (bench.py roofline): event pairs recorded
+    // on the launching stream around every k_accumulate launch while enabled
+    std::atomic<int> prof_enabled{0};
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_events;
 };
 Context &ctx();
 

@@ -93,8 +93,19 @@ static int32_t msm_run(const void *bases_dev, const void *scalars_dev, size_t n,
     DG_LAUNCH(k_scan_add, sb, 1024, 0, s, off, bsums, hist, g.nb, cursor);
     DG_LAUNCH(k_digits<1>, gd, 256, 0, s, (const uint32_t *)scalars_dev, (uint32_t)n, g, cursor, entries, err_flag);
 
+    cudaEvent_t pe0 = nullptr, pe1 = nullptr;
+    if (ctx().prof_enabled.load()) {
+        DG_CUDA(cudaEventCreate(&pe0));
+        DG_CUDA(cudaEventCreate(&pe1));
+        DG_CUDA(cudaEventRecord(pe0, s));
+    }
     DG_LAUNCH(k_accumulate<F>, div_up(m.nchunks, 128), 128, 0, s, (const Affine<F> *)bases_dev, entries, off, g.nb, m.L,
               buckets, head, tail);
+    if (pe0) {
+        DG_CUDA(cudaEventRecord(pe1, s));
+        std::lock_guard<std::mutex> lk(ctx().mu);
+        ctx().prof_events.emplace_back(pe0, pe1);
+    }
     DG_LAUNCH(k_bucket_fixup<F>, div_up(g.nb, 128), 128, 0, s, off, g.nb, m.L, buckets, head, tail);
 
     // multi-level bucket reduction

@@ -26,6 +26,7 @@ EXPORTS = [
     'dg_multi_miller_loop', 'dg_final_exponentiation', 'dg_multi_pairing', 'dg_multi_pairing_is_one',
     'dg_gt_pow', 'dg_fp12_mul',
     'dg_fold_g1', 'dg_fold_g1_device', 'dg_fold_g2',
+    'dg_prof_enable', 'dg_prof_read_accumulate',
     'dg_dbg_fp_op',
 ]
 
@@ -136,6 +137,17 @@ def msm_device(bases_ptr, scalars_ptr, n, out_ptr, stream=0, g2=False):
     lib = init()
     fn = lib.dg_msm_g2_device if g2 else lib.dg_msm_g1_device
     _check(fn(C.c_void_p(bases_ptr), C.c_void_p(scalars_ptr), C.c_size_t(n), C.c_void_p(out_ptr), C.c_void_p(stream)))
+
+
+def prof_enable(on):
+    _check(init().dg_prof_enable(C.c_int32(1 if on else 0)))
+
+
+def prof_read_accumulate():
+    """-> (mean ms of the k_accumulate launches since the last read, launch count)."""
+    ms, cnt = C.c_double(0), C.c_int32(0)
+    _check(init().dg_prof_read_accumulate(C.byref(ms), C.byref(cnt)))
+    return ms.value, cnt.value
 
 
 def msm_set_window(c):

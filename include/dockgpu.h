@@ -135,6 +135,13 @@ int32_t dg_fold_g1(const uint8_t *jac_points, size_t k, uint8_t *out_jac);
 int32_t dg_fold_g1_device(const void *jac_points_dev, size_t k, void *out_jac_dev, void *stream);
 int32_t dg_fold_g2(const uint8_t *jac_points, size_t k, uint8_t *out_jac);
 
+/* ---- measurement hooks (bench.py) ---------------------------------------------------------------
+ * While enabled, every MSM records a CUDA-event pair on its launching stream around the bucket
+ * accumulation kernel (the dominant kernel); dg_prof_read_accumulate synchronises the device,
+ * returns the mean duration of the launches recorded since the last read, and clears the list. */
+int32_t dg_prof_enable(int32_t on);
+int32_t dg_prof_read_accumulate(double *mean_ms, int32_t *count);
+
 /* ---- test hooks (field arithmetic parity; not part of the reference-facing surface) ---------- */
 int32_t dg_dbg_fp_op(int32_t op, const uint8_t *a, const uint8_t *b, size_t n, uint8_t *out);
 

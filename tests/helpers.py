@@ -34,11 +34,11 @@ def ints_of(scalar_bytes):
 
 def affine_g1(jac):
     """Canonical affine bytes of Jacobian G1 record(s) via the oracle (the comparison form)."""
-    return bytes(cref.normalize_batch_g1(np.asarray(jac, dtype=np.uint8)))
+    return bytes(cref.normalize_batch_g1(cref._as_np(jac)))
 
 
 def affine_g2(jac):
-    return bytes(cref.normalize_batch_g2(np.asarray(jac, dtype=np.uint8)))
+    return bytes(cref.normalize_batch_g2(cref._as_np(jac)))
 
 
 def known_dlog_msm_g1(ks, ss):
