@@ -17,8 +17,7 @@ static inline MsmGeom msm_geometry(size_t n) {
         c = ceil_log2_sz(n ? n : 1) - 4;
         if (c < 4) c = 4;
         if (c > 20) c = 20;
-        if (c == 15) c = 16;          // 16 x 16 = 256 exactly: one window fewer than c = 15
-        if (c == 14) c = 13;          // 20 windows instead of 19 but half the buckets
+        if (c >= 13 && c <= 19) c = 16;   // measured on B200 (tools/sweep_c.py): 16 x 16 = 256 bits exactly wins from 2^17 to 2^23
     }
     MsmGeom g;
     g.c = c;
@@ -31,7 +30,7 @@ static inline MsmGeom msm_geometry(size_t n) {
 struct MsmLayout {
     MsmGeom g;
     uint32_t L, nchunks, ngroups1;
-    size_t o_hist, o_off, o_cursor, o_bsums, o_entries, o_buckets, o_head, o_tail, o_red[4], total;
+    size_t o_hist, o_off, o_cursor, o_bsums, o_entries, o_buckets, o_head, o_tail, o_long, o_red[4], total;
 };
 
 template <class F> static inline MsmLayout msm_layout(size_t n) {
@@ -57,6 +56,7 @@ template <class F> static inline MsmLayout msm_layout(size_t n) {
     m.o_buckets = take(sizeof(XYZZ<F>) * m.g.nb);
     m.o_head = take(sizeof(XYZZ<F>) * m.nchunks);
     m.o_tail = take(sizeof(XYZZ<F>) * m.nchunks);
+    m.o_long = take(sizeof(uint32_t) * (m.nchunks / DG_LONG_PIECES + 64));     // [0] = count, list from [16]
     for (int k = 0; k < 4; k++) m.o_red[k] = take(sizeof(XYZZ<F>) * (size_t)m.g.nwin * m.ngroups1);
     m.total = o;
     return m;
@@ -106,7 +106,11 @@ static int32_t msm_run(const void *bases_dev, const void *scalars_dev, size_t n,
         std::lock_guard<std::mutex> lk(ctx().mu);
         ctx().prof_events.emplace_back(pe0, pe1);
     }
-    DG_LAUNCH(k_bucket_fixup<F>, div_up(g.nb, 128), 128, 0, s, off, g.nb, m.L, buckets, head, tail);
+    uint32_t *long_count = (uint32_t *)(scratch + m.o_long), *long_list = long_count + 16;
+    DG_CUDA(cudaMemsetAsync(long_count, 0, 64, s));
+    DG_LAUNCH(k_bucket_fixup<F>, div_up(g.nb, 128), 128, 0, s, off, g.nb, m.L, buckets, head, tail, long_count, long_list);
+    DG_LAUNCH(k_bucket_fixup_long<F>, 2 * ctx().sm_count, 128, sizeof(XYZZ<F>) * 128, s, off, m.L, buckets, head, tail,
+              long_count, long_list);
 
     // multi-level bucket reduction
     const XYZZ<F> *x = buckets, *y = nullptr;

@@ -172,10 +172,15 @@ __global__ void __launch_bounds__(128, 3) k_accumulate(const Affine<F> *__restri
     if (first) xyzz_store(&head[t], acc); else xyzz_store(&tail[t], acc);
 }
 
+// Buckets whose pieces span more than DG_LONG_PIECES chunks (hot buckets: skewed scalars such as
+// the 0/1-heavy witnesses of real circuits, or the sparsely populated top window) are queued for
+// k_bucket_fixup_long instead of being summed by one thread.
+#define DG_LONG_PIECES 24
 template <class F>
 __global__ void __launch_bounds__(128) k_bucket_fixup(const uint32_t *__restrict__ off, uint32_t nb, uint32_t L,
                                                       XYZZ<F> *__restrict__ buckets, const XYZZ<F> *__restrict__ head,
-                                                      const XYZZ<F> *__restrict__ tail) {
+                                                      const XYZZ<F> *__restrict__ tail, uint32_t *__restrict__ long_count,
+                                                      uint32_t *__restrict__ long_list) {
     uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= nb) return;
     uint32_t s = off[b], e = off[b + 1], M = off[nb];
@@ -189,9 +194,45 @@ __global__ void __launch_bounds__(128) k_bucket_fixup(const uint32_t *__restrict
         else if (last0) xyzz_store(&buckets[b], xyzz_load<F>(&tail[t0]));
         return;                                     // middle run: already written by k_accumulate
     }
+    if (t1 - t0 > DG_LONG_PIECES) {
+        long_list[atomicAdd(long_count, 1u)] = b;
+        return;
+    }
     XYZZ<F> acc = first0 ? xyzz_load<F>(&head[t0]) : xyzz_load<F>(&tail[t0]);
     for (uint32_t t = t0 + 1; t <= t1; t++) acc = xyzz_add(acc, xyzz_load<F>(&head[t]));
     xyzz_store(&buckets[b], acc);
+}
+
+// One CTA per queued bucket: 128 threads each sum a contiguous slice of the pieces, then a
+// shared-memory tree combines the 128 partial sums.
+template <class F>
+__global__ void __launch_bounds__(128) k_bucket_fixup_long(const uint32_t *__restrict__ off, uint32_t L,
+                                                           XYZZ<F> *__restrict__ buckets, const XYZZ<F> *__restrict__ head,
+                                                           const XYZZ<F> *__restrict__ tail, const uint32_t *__restrict__ long_count,
+                                                           const uint32_t *__restrict__ long_list) {
+    extern __shared__ __align__(16) unsigned char dg_smem_long[];
+    XYZZ<F> *sm = reinterpret_cast<XYZZ<F> *>(dg_smem_long);
+    uint32_t k = threadIdx.x, cnt = *long_count;
+    for (uint32_t i = blockIdx.x; i < cnt; i += gridDim.x) {
+        uint32_t b = long_list[i];
+        uint32_t s = off[b], e = off[b + 1];
+        uint32_t t0 = s / L, t1 = (e - 1) / L, np = t1 - t0 + 1;
+        bool first0 = (s == t0 * L);
+        uint32_t per = (np + 127) / 128, lo = k * per, hi = lo + per < np ? lo + per : np;
+        XYZZ<F> acc = xyzz_inf<F>();
+        for (uint32_t j = lo; j < hi; j++) {
+            const XYZZ<F> *src = (j == 0 && !first0) ? &tail[t0] : &head[t0 + j];
+            acc = xyzz_add(acc, xyzz_load<F>(src));
+        }
+        sm[k] = acc;
+        __syncthreads();
+        for (uint32_t st = 64; st > 0; st >>= 1) {
+            if (k < st) sm[k] = xyzz_add(sm[k], sm[k + st]);
+            __syncthreads();
+        }
+        if (k == 0) xyzz_store(&buckets[b], sm[0]);
+        __syncthreads();
+    }
 }
 
 // ---------------------------------------------------------------- bucket reduction -----------
