@@ -122,13 +122,14 @@ static int32_t msm_run(const void *bases_dev, const void *scalars_dev, size_t n,
         uint32_t cnt = cnt_x > cnt_y ? cnt_x : cnt_y;
         uint32_t ngroups = (cnt + (1u << log_g) - 1) >> log_g;
         XYZZ<F> *xo = red[2 * pp], *yo = red[2 * pp + 1];
-        DG_LAUNCH(k_reduce_level<F>, div_up((size_t)ngroups * g.nwin, 128), 128, 0, s, x, cnt_x, stride_x, y, cnt_y, stride_y,
-                  log_g, ngroups, g.nwin, xo, yo, m.ngroups1);
+        const unsigned qpb = sizeof(F) > 48 ? 8 : 16;            // quads per CTA (shared-memory workspace per quad)
+        DG_LAUNCH(k_reduce_level<F>, div_up((size_t)ngroups * g.nwin, qpb), qpb * 4, sizeof(QuadWS<F>) * qpb, s, x, cnt_x,
+                  stride_x, y, cnt_y, stride_y, log_g, ngroups, g.nwin, xo, yo, m.ngroups1);
         if (ngroups == 1) { wsum = yo; break; }
         x = xo; y = yo; cnt_x = ngroups - 1; cnt_y = ngroups; stride_x = stride_y = m.ngroups1;
         pp ^= 1;
     }
-    DG_LAUNCH(k_window_combine<F>, 1, 32, 0, s, wsum, m.ngroups1, g.nwin, g.c, (Jac<F> *)out_jac_dev);
+    DG_LAUNCH(k_window_combine<F>, 1, 32, sizeof(QuadWS<F>), s, wsum, m.ngroups1, g.nwin, g.c, (Jac<F> *)out_jac_dev);
     DG_CUDA(cudaGetLastError());
     return DG_OK;
 }

@@ -17,6 +17,7 @@
 //   7 k_window_combine  Horner over windows, result as Jacobian (ark Projective layout)
 #pragma once
 #include "ec.cuh"
+#include "quad.cuh"
 
 namespace dg {
 
@@ -236,51 +237,72 @@ __global__ void __launch_bounds__(128) k_bucket_fixup_long(const uint32_t *__res
 }
 
 // ---------------------------------------------------------------- bucket reduction -----------
-// One level of  S = sum_j (j+1) x_j + sum_j y_j  per window.  Thread (w, q) folds the g items
-// x[q*g .. q*g+g) with a running sum:  A = sum (k+1) x_{qg+k},  R = sum x_{qg+k},  Y = sum y.
+// One level of  S = sum_j (j+1) x_j + sum_j y_j  per window.  QUAD (w, q) - four lanes sharing
+// every point operation, see quad.cuh - folds the g items x[q*g .. q*g+g) with a running sum:
+//   A = sum (k+1) x_{qg+k},  R = sum x_{qg+k},  Y = sum y.
 // Then  S = sum_q (A_q + Y_q) + sum_{q>=1} q * (g R_q):  the next level's y'_q = A_q + Y_q and
 // x'_{q-1} = g * R_q (log2 g doublings).  Items past the end are the identity.
 template <class F>
-__global__ void __launch_bounds__(128) k_reduce_level(const XYZZ<F> *__restrict__ x, uint32_t cnt_x, uint32_t stride_x,
-                                                      const XYZZ<F> *__restrict__ y, uint32_t cnt_y, uint32_t stride_y,
-                                                      int log_g, uint32_t ngroups, int nwin,
-                                                      XYZZ<F> *__restrict__ xo, XYZZ<F> *__restrict__ yo, uint32_t stride_o) {
-    uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
-    if (tid >= ngroups * (uint32_t)nwin) return;
-    uint32_t w = tid / ngroups, q = tid % ngroups, g = 1u << log_g;
+__global__ void __launch_bounds__(64) k_reduce_level(const XYZZ<F> *__restrict__ x, uint32_t cnt_x, uint32_t stride_x,
+                                                     const XYZZ<F> *__restrict__ y, uint32_t cnt_y, uint32_t stride_y,
+                                                     int log_g, uint32_t ngroups, int nwin,
+                                                     XYZZ<F> *__restrict__ xo, XYZZ<F> *__restrict__ yo, uint32_t stride_o) {
+    extern __shared__ __align__(16) unsigned char dg_smem_quad[];
+    QuadWS<F> &ws = reinterpret_cast<QuadWS<F> *>(dg_smem_quad)[threadIdx.x >> 2];
+    QuadCtx qc = quad_ctx();
+    uint32_t gid = blockIdx.x * (blockDim.x >> 2) + (threadIdx.x >> 2);
+    if (gid >= ngroups * (uint32_t)nwin) return;          // whole quad leaves together
+    uint32_t w = gid / ngroups, q = gid % ngroups, g = 1u << log_g;
     const XYZZ<F> *xw = x + (size_t)w * stride_x;
-    XYZZ<F> run = xyzz_inf<F>(), acc = xyzz_inf<F>();
+    enum { RUN = 0, ACC = 1, ITEM = 2 };
+    quad_set_inf(ws, RUN, qc);
+    quad_set_inf(ws, ACC, qc);
     for (uint32_t k = g; k-- > 0;) {
         uint32_t j = q * g + k;
-        if (j < cnt_x) run = xyzz_add(run, xyzz_load<F>(&xw[j]));
-        acc = xyzz_add(acc, run);
+        if (j < cnt_x) {
+            quad_load(ws, ITEM, &xw[j], qc);
+            quad_add(ws, RUN, RUN, ITEM, qc);
+        }
+        quad_add(ws, ACC, ACC, RUN, qc);
     }
     if (cnt_y) {
         const XYZZ<F> *yw = y + (size_t)w * stride_y;
         for (uint32_t k = 0; k < g; k++) {
             uint32_t j = q * g + k;
-            if (j < cnt_y) acc = xyzz_add(acc, xyzz_load<F>(&yw[j]));
+            if (j < cnt_y) {
+                quad_load(ws, ITEM, &yw[j], qc);
+                quad_add(ws, ACC, ACC, ITEM, qc);
+            }
         }
     }
-    xyzz_store(&yo[(size_t)w * stride_o + q], acc);
+    quad_store(ws, ACC, &yo[(size_t)w * stride_o + q], qc);
     if (q >= 1) {
         for (int k = 0; k < log_g; k++)
-            if (!xyzz_is_inf(run)) run = xyzz_dbl(run);
-        xyzz_store(&xo[(size_t)w * stride_o + q - 1], run);
+            if (!fis_zero(ws.v[4 * RUN + 2])) quad_dbl(ws, RUN, RUN, qc);
+        quad_store(ws, RUN, &xo[(size_t)w * stride_o + q - 1], qc);
     }
 }
 
-// window sums S_w (one XYZZ per window at stride) -> sum_w 2^(c w) S_w, Horner from the top.
+// window sums S_w (one XYZZ per window at stride) -> sum_w 2^(c w) S_w, Horner from the top,
+// by one quad (the only unavoidable serial chain of the MSM: c * (nwin - 1) doublings).
 template <class F>
-__global__ void k_window_combine(const XYZZ<F> *__restrict__ wsum, uint32_t stride, int nwin, int c, Jac<F> *out) {
-    if (threadIdx.x != 0 || blockIdx.x != 0) return;
-    XYZZ<F> acc = xyzz_load<F>(&wsum[(size_t)(nwin - 1) * stride]);
+__global__ void __launch_bounds__(32) k_window_combine(const XYZZ<F> *__restrict__ wsum, uint32_t stride, int nwin, int c, Jac<F> *out) {
+    extern __shared__ __align__(16) unsigned char dg_smem_quad[];
+    QuadWS<F> &ws = reinterpret_cast<QuadWS<F> *>(dg_smem_quad)[0];
+    if (threadIdx.x >= 4 || blockIdx.x != 0) return;
+    QuadCtx qc = quad_ctx();
+    enum { ACC = 1, ITEM = 2 };
+    quad_load(ws, ACC, &wsum[(size_t)(nwin - 1) * stride], qc);
     for (int w = nwin - 2; w >= 0; w--) {
         for (int k = 0; k < c; k++)
-            if (!xyzz_is_inf(acc)) acc = xyzz_dbl(acc);
-        acc = xyzz_add(acc, xyzz_load<F>(&wsum[(size_t)w * stride]));
+            if (!fis_zero(ws.v[4 * ACC + 2])) quad_dbl(ws, ACC, ACC, qc);
+        quad_load(ws, ITEM, &wsum[(size_t)w * stride], qc);
+        quad_add(ws, ACC, ACC, ITEM, qc);
     }
-    jac_store(out, xyzz_to_jac(acc));
+    if (threadIdx.x == 0) {
+        XYZZ<F> r = {ws.v[4 * ACC], ws.v[4 * ACC + 1], ws.v[4 * ACC + 2], ws.v[4 * ACC + 3]};
+        jac_store(out, xyzz_to_jac(r));
+    }
 }
 
 }  // namespace dg
