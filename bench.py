@@ -8,10 +8,15 @@ A "step" is one G1 MSM over synthetic seeded scalars/bases (bases k_i*G with kno
 uniform in [0, r)).  N = 1: 2^20 terms (the size the metric is quoted on).  N > 1: weak scaling,
 every rank owns a contiguous 2^20-term base range of one N*2^20-term MSM; partial results are
 all-gathered (NCCL, 144 B per rank) and folded on the GPU under the group law.
-`value`   : terms/s with scalars and bases already resident in HBM (device-pointer C-ABI call).
+`value`   : terms/s with scalars and bases already resident in HBM (dg_msm_g1_handle_device).
+            Bases live behind a handle as in the reference's workloads (proving keys / signature
+            parameters are fixed across calls) with the 2^(20k)-multiples table built
+            once at upload (dg_bases_precompute, 13 x the base memory).  `value_plain_bases` is the
+            same MSM through dg_msm_g1_device on the raw 96-byte bases with nothing precomputed.
 `e2e`     : terms/s through the host C-ABI call dg_msm_g1 with the scalars in pinned host memory
-            copied every step (bases resident behind a handle: the proving-key model)
-            and the 144-byte result read back every step.
+            copied every step and the 144-byte result read back every step (same handle);
+            `e2e_plain_bases` likewise without the precomputed table.
+--total-logn T switches to strong scaling: one 2^T-term MSM split over the ranks.
 `roofline`: the dominant kernel (k_accumulate) against the measured HBM peak, algorithmic bytes
             128 B/term; `int_roofline` is the integer-pipe reading of the same launch.
 `cpu_baseline`: the oracle's C restatement of the arkworks rayon algorithm on the host cores.
@@ -115,7 +120,7 @@ def run_reference(args, rank, world):
     msm_bigint_wnaf, OpenMP over windows like rayon) on the host cores, same config/metric."""
     if rank != 0:
         return
-    n = 1 << args.logn
+    n = 1 << (args.total_logn if args.total_logn else args.logn)
     bases, scalars, ks = synth_inputs(n)
     cores = host_cores()
     os.environ.setdefault('OMP_NUM_THREADS', str(cores))
@@ -159,7 +164,11 @@ def run_ours(args, rank, world, local_rank):
     torch.cuda.set_device(local_rank)
     dev = torch.device('cuda', local_rank)
     lib.init(local_rank)
-    n = 1 << args.logn                       # terms per rank
+    strong = args.total_logn > 0
+    if strong:
+        n = (1 << args.total_logn) // world  # strong scaling: fixed global MSM split by base range
+    else:
+        n = 1 << args.logn                   # weak scaling: terms per rank
     bases, scalars, ks = synth_inputs(n, rank)
     d_bases = torch.from_numpy(bases).to(dev)
     d_scalars = torch.from_numpy(scalars).to(dev)
@@ -170,8 +179,15 @@ def run_ours(args, rank, world, local_rank):
     stream = torch.cuda.Stream(device=dev)
     torch.cuda.set_stream(stream)
 
+    hb = lib.Bases(bases)
+    hb_pre = lib.Bases(bases).precompute(args.precompute_window)
+    mode = {'pre': True}
+
     def step():
-        lib.msm_device(d_bases.data_ptr(), d_scalars.data_ptr(), n, d_out.data_ptr(), stream.cuda_stream)
+        if mode['pre']:
+            lib.msm_handle_device(hb_pre, d_scalars.data_ptr(), n, d_out.data_ptr(), stream.cuda_stream)
+        else:
+            lib.msm_device(d_bases.data_ptr(), d_scalars.data_ptr(), n, d_out.data_ptr(), stream.cuda_stream)
         if world > 1:
             dist.all_gather_into_tensor(d_gather, d_out)
             lib.fold_g1_device(d_gather.data_ptr(), world, d_final.data_ptr(), stream.cuda_stream)
@@ -181,16 +197,36 @@ def run_ours(args, rank, world, local_rank):
             dist.barrier()
         torch.cuda.synchronize()
 
-    for _ in range(args.warmup):
-        flush.fill_(1)
-        step()
-    barrier()
-
-    # correctness gate before timing: known-discrete-log identity on this rank's shard
+    # correctness gate before timing: known-discrete-log identity on this rank's shard, both paths
     from oracle import cref
-    got = bytes(cref.normalize_batch_g1(d_out.cpu().numpy()))
-    if got != known_dlog_expected(ks, scalars):
-        raise SystemExit('bench: GPU MSM result differs from the known-dlog identity')
+    expected = known_dlog_expected(ks, scalars)
+    for pre in (False, True):
+        mode['pre'] = pre
+        for _ in range(args.warmup):
+            flush.fill_(1)
+            step()
+        barrier()
+        got = bytes(cref.normalize_batch_g1(d_out.cpu().numpy()))
+        if got != expected:
+            raise SystemExit('bench: GPU MSM result differs from the known-dlog identity (precomputed=%s)' % pre)
+
+    def timed(pre):
+        mode['pre'] = pre
+        evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+        barrier()
+        for e0, e1 in evs:
+            flush.fill_(1)                   # L2 flush between timed iterations (outside the event pair)
+            e0.record(stream)
+            step()
+            e1.record(stream)
+        barrier()
+        ms = sum(e0.elapsed_time(e1) for e0, e1 in evs)
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    plain_ms = timed(False)
 
     sampler = ClockSampler(local_rank)
     if rank == 0:
@@ -198,47 +234,40 @@ def run_ours(args, rank, world, local_rank):
     lib.prof_enable(True)
     lib.prof_read_accumulate()
     launches0 = lib.launch_count()
-    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-    barrier()
-    for e0, e1 in evs:
-        flush.fill_(1)                       # L2 flush between timed iterations (outside the event pair)
-        e0.record(stream)
-        step()
-        e1.record(stream)
-    barrier()
+    total_ms = timed(True)
     launches = lib.launch_count() - launches0
     acc_ms, acc_cnt = lib.prof_read_accumulate()
     lib.prof_enable(False)
     clocks = sampler.stop() if rank == 0 else None
-    total_ms = sum(e0.elapsed_time(e1) for e0, e1 in evs)
-    t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    total_ms = float(t.item())
     value = n * world * args.steps / (total_ms * 1e-3)
+    value_plain = n * world * args.steps / (plain_ms * 1e-3)
 
     # ---- e2e: host C-ABI call, scalars from pinned host memory every step, result read back ----
-    hb = lib.Bases(bases)
     pinned = torch.from_numpy(scalars.copy()).pin_memory()
     pin_np = pinned.numpy()
-    for _ in range(2):
-        lib.msm(hb, pin_np)
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        out_host = lib.msm(hb, pin_np)
+
+    def e2e(handle):
+        for _ in range(2):
+            lib.msm(handle, pin_np)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            out_host = lib.msm(handle, pin_np)
+            if world > 1:
+                part = torch.from_numpy(np.array(out_host)).to(dev)
+                dist.all_gather_into_tensor(d_gather, part)
+                lib.fold_g1_device(d_gather.data_ptr(), world, d_final.data_ptr(), stream.cuda_stream)
+                d_final.cpu()
+        torch.cuda.synchronize()
+        te = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
         if world > 1:
-            part = torch.from_numpy(np.array(out_host)).to(dev)
-            dist.all_gather_into_tensor(d_gather, part)
-            lib.fold_g1_device(d_gather.data_ptr(), world, d_final.data_ptr(), stream.cuda_stream)
-            d_final.cpu()
-    torch.cuda.synchronize()
-    e2e_s = time.perf_counter() - t0
-    te = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(te, op=dist.ReduceOp.MAX)
-    e2e_value = n * world * args.steps / float(te.item())
+            dist.all_reduce(te, op=dist.ReduceOp.MAX)
+        return n * world * args.steps / float(te.item())
+
+    e2e_plain = e2e(hb)
+    e2e_value = e2e(hb_pre)
     hb.free()
+    hb_pre.free()
 
     if rank != 0:
         return
@@ -252,17 +281,22 @@ def run_ours(args, rank, world, local_rank):
     ncu = load_profile_json('ncu_accumulate.json') or {}
     ip = load_profile_json('int_peak_r01.json') or {}
     imad_peak = (ip.get('imad_lo') or {}).get('ops_per_s')
-    nwin = 16 if args.logn >= 19 else None
+    pre_c = args.precompute_window if args.precompute_window else (20 if n >= (1 << 18) else 16)
+    nwin = (256 + pre_c - 1) // pre_c
     line = {
         'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
-        'ms_per_step': total_ms / args.steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
-        'dtype': 'u32', 'data': 'synthetic',
-        'config': {'workload': 'bls12-381 g1 msm, 2^%d random scalars/bases per GPU' % args.logn, 'terms_per_gpu': n,
+        'ms_per_step': total_ms / args.steps, 'higher_is_better': True, 'scaling': 'strong' if strong else 'weak',
+        'vs_baseline': None, 'dtype': 'u32', 'data': 'synthetic',
+        'value_plain_bases': value_plain, 'ms_per_step_plain_bases': plain_ms / args.steps,
+        'config': {'workload': 'bls12-381 g1 msm, 2^%.3g random scalars/bases per GPU' % np.log2(n), 'terms_per_gpu': n,
                    'global_terms': n * world, 'parallelism': 'base-range shards x%d + all-gather/fold' % world,
+                   'bases': 'resident behind a handle, 2^(%d k)-multiples table (%d rows) built once at upload; '
+                            'value_plain_bases = raw bases, nothing precomputed' % (pre_c, nwin),
                    'l2': 'flushed between timed iterations (256 MiB fill)', 'result_check': 'known-dlog identity, bit-exact'},
         'clocks': clocks,
         'e2e': {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': 32 * n, 'd2h_bytes_per_step': 144,
                 'note': 'dg_msm_g1 host call; scalars from pinned host memory every step; bases resident (handle)'},
+        'e2e_plain_bases': e2e_plain,
         'gpu_launches': int(launches),
         'roofline': {'bound': 'hbm', 'kernel': 'k_accumulate<Fp>', 'achieved': achieved, 'peak': hbm_peak, 'unit': 'GB/s',
                      'frac': (achieved / hbm_peak) if achieved else None, 'traffic': ncu.get('dram_bytes_per_launch'),
@@ -295,6 +329,8 @@ def main():
     ap.add_argument('--logn', type=int, default=20, help='log2 of the terms per GPU')
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--no-cpu', action='store_true', help='skip the cpu_baseline leg')
+    ap.add_argument('--total-logn', type=int, default=0, help='strong scaling: log2 of the GLOBAL term count')
+    ap.add_argument('--precompute-window', type=int, default=0, help='window bits of the resident table (0 = default)')
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == 'ours':
         args.warmup = 3

@@ -20,6 +20,10 @@ __global__ void __launch_bounds__(128) k_dbg_fp_op(int op, const Fp *a, const Fp
 }
 }  // namespace dg
 
+namespace dg {
+int32_t bases_precompute_g1(HandleRec &rec, int c, cudaStream_t s) { return bases_precompute<Fp>(rec, c, s); }
+}
+
 extern "C" {
 int32_t dg_fixed_base_table_g1(const uint8_t *p, size_t hint_n, uint64_t *h) { return fixed_table_build<Fp>(p, hint_n, h); }
 int32_t dg_fixed_base_mul_many_g1(uint64_t h, const uint8_t *s, size_t m, uint8_t *o) { return fixed_mul_many<Fp>(h, s, m, o); }

@@ -1,6 +1,9 @@
 // G2 entry points of the batch group operations.
 #include "batch_host.cuh"
 using namespace dg;
+namespace dg {
+int32_t bases_precompute_g2(HandleRec &rec, int c, cudaStream_t s) { return bases_precompute<Fp2>(rec, c, s); }
+}
 extern "C" {
 int32_t dg_fixed_base_table_g2(const uint8_t *p, size_t hint_n, uint64_t *h) { return fixed_table_build<Fp2>(p, hint_n, h); }
 int32_t dg_fixed_base_mul_many_g2(uint64_t h, const uint8_t *s, size_t m, uint8_t *o) { return fixed_mul_many<Fp2>(h, s, m, o); }

@@ -149,6 +149,37 @@ template <class F> static int32_t normalize_host(const uint8_t *jac, size_t m, u
     return DG_OK;
 }
 
+// dg_bases_precompute: replace the resident bases by the table {2^(c*k) * P_i}, k < ceil(256/c)
+template <class F> static int32_t bases_precompute(HandleRec &rec, int c, cudaStream_t s) {
+    if (rec.window) return fail(DG_ERR_BAD_ARG, "bases_precompute: handle already holds a precomputed table");
+    if (c < 8 || c > 24) return fail(DG_ERR_BAD_ARG, "bases_precompute: window must be in [8, 24]");
+    int rows = (256 + c - 1) / c;
+    size_t n = rec.n;
+    if ((uint64_t)n * rows >= (1ull << 31)) return fail(DG_ERR_BAD_ARG, "bases_precompute: table exceeds 2^31 points");
+    Affine<F> *table = nullptr;
+    Jac<F> *jac = nullptr;
+    F *prefix = nullptr;
+    size_t extra = n * (size_t)(rows - 1);
+    DG_CUDA(cudaMalloc(&table, Sizes<F>::AFF * n * rows));
+    cudaError_t e = cudaMalloc(&jac, Sizes<F>::JAC * extra);
+    if (e == cudaSuccess) e = cudaMalloc(&prefix, sizeof(F) * extra);
+    if (e != cudaSuccess) {
+        cudaFree(table); cudaFree(jac); cudaFree(prefix);
+        return fail(DG_ERR_OOM, std::string("bases_precompute: ") + cudaGetErrorString(e));
+    }
+    cudaMemcpyAsync(table, rec.dev, Sizes<F>::AFF * n, cudaMemcpyDeviceToDevice, s);
+    DG_LAUNCH(k_precompute_rows<F>, div_up(n, 128), 128, 0, s, (const Affine<F> *)rec.dev, (uint32_t)n, c, rows, jac);
+    normalize_device<F>(jac, extra, table + n, prefix, s);
+    e = cudaStreamSynchronize(s);
+    cudaFree(jac); cudaFree(prefix);
+    if (e != cudaSuccess) { cudaFree(table); return fail(DG_ERR_CUDA, cudaGetErrorString(e)); }
+    cudaFree(rec.dev);
+    rec.dev = table;
+    rec.window = c;
+    rec.nwin = rows;
+    return DG_OK;
+}
+
 template <class F> static int32_t fold_host(const uint8_t *jac, size_t k, uint8_t *out_jac) {
     int32_t rc = check_init();
     if (rc) return rc;

@@ -182,6 +182,21 @@ __global__ void __launch_bounds__(128) k_normalize(const Jac<F> *__restrict__ in
     }
 }
 
+// ---- precomputed multiples for resident bases ------------------------------------------------
+// row k (k >= 1) of the table is 2^(c*k) * P_i; thread i walks its own doubling chain.
+template <class F>
+__global__ void __launch_bounds__(128) k_precompute_rows(const Affine<F> *__restrict__ bases, uint32_t n, int c, int rows,
+                                                         Jac<F> *__restrict__ out) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    Affine<F> p = aff_load<F>(&bases[i]);
+    Jac<F> cur = aff_is_inf(p) ? jac_inf<F>() : Jac<F>{p.x, p.y, fone<F>()};
+    for (int k = 1; k < rows; k++) {
+        for (int t = 0; t < c; t++) cur = jac_dbl(cur);
+        jac_store(&out[(size_t)(k - 1) * n + i], cur);
+    }
+}
+
 // ---- fold ----------------------------------------------------------------------------------------
 template <class F> __global__ void k_fold_jac(const Jac<F> *in, uint32_t k, Jac<F> *out) {
     if (threadIdx.x != 0 || blockIdx.x != 0) return;

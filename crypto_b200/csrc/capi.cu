@@ -78,6 +78,7 @@ static int32_t msm_host(uint64_t handle, const uint8_t *bases, const uint8_t *sc
     if ((handle != 0) == (bases != nullptr) && n) return fail(DG_ERR_BAD_ARG, "msm: give exactly one of bases_handle / bases");
     ThreadState &t = tls();
     const void *bases_dev = nullptr;
+    MsmPre pre = {0, 0};
     if (handle) {
         std::lock_guard<std::mutex> lk(ctx().mu);
         auto it = ctx().handles.find(handle);
@@ -85,8 +86,9 @@ static int32_t msm_host(uint64_t handle, const uint8_t *bases, const uint8_t *sc
             return fail(DG_ERR_BAD_ARG, "msm: bad bases handle");
         if (n > it->second.n) return fail(DG_ERR_BAD_ARG, "msm: n exceeds uploaded bases");
         bases_dev = it->second.dev;
+        if (it->second.window) pre = {it->second.window, (uint32_t)it->second.n};
     }
-    size_t need = (G2 ? msm_scratch_bytes_g2(n) : msm_scratch_bytes_g1(n)) + Arena::pad(32 * n) + Arena::pad(JAC) +
+    size_t need = (G2 ? msm_scratch_bytes_g2(n, pre) : msm_scratch_bytes_g1(n, pre)) + Arena::pad(32 * n) + Arena::pad(JAC) +
                   (handle ? 0 : Arena::pad(PT * n));
     rc = t.arena.ensure(need, t.stream);
     if (rc) return rc;
@@ -99,26 +101,36 @@ static int32_t msm_host(uint64_t handle, const uint8_t *bases, const uint8_t *sc
         bases_dev = d_bases;
     }
     char *scratch = t.arena.alloc<char>(need - t.arena.used);
-    rc = G2 ? msm_run_g2(bases_dev, d_scalars, n, d_out, scratch, t.err_flag, t.stream)
-            : msm_run_g1(bases_dev, d_scalars, n, d_out, scratch, t.err_flag, t.stream);
+    rc = G2 ? msm_run_g2(bases_dev, d_scalars, n, d_out, scratch, t.err_flag, t.stream, pre)
+            : msm_run_g1(bases_dev, d_scalars, n, d_out, scratch, t.err_flag, t.stream, pre);
     if (rc) return rc;
     DG_CUDA(cudaMemcpyAsync(out_jac, d_out, JAC, cudaMemcpyDeviceToHost, t.stream));
     return read_err_flag(t, "msm");
 }
 
 template <bool G2>
-static int32_t msm_device(const void *bases_dev, const void *scalars_dev, size_t n, void *out_jac_dev, void *stream) {
+static int32_t msm_device(uint64_t handle, const void *bases_dev, const void *scalars_dev, size_t n, void *out_jac_dev, void *stream) {
     int32_t rc = check_init();
     if (rc) return rc;
+    MsmPre pre = {0, 0};
+    if (handle) {
+        std::lock_guard<std::mutex> lk(ctx().mu);
+        auto it = ctx().handles.find(handle);
+        if (it == ctx().handles.end() || it->second.kind != (G2 ? HandleRec::BASES_G2 : HandleRec::BASES_G1))
+            return fail(DG_ERR_BAD_ARG, "msm_device: bad bases handle");
+        if (n > it->second.n) return fail(DG_ERR_BAD_ARG, "msm_device: n exceeds uploaded bases");
+        bases_dev = it->second.dev;
+        if (it->second.window) pre = {it->second.window, (uint32_t)it->second.n};
+    }
     if (!out_jac_dev || (n && (!bases_dev || !scalars_dev))) return fail(DG_ERR_BAD_ARG, "msm_device: null pointer");
     ThreadState &t = tls();
     cudaStream_t s = stream ? (cudaStream_t)stream : t.stream;
-    size_t need = G2 ? msm_scratch_bytes_g2(n) : msm_scratch_bytes_g1(n);
+    size_t need = G2 ? msm_scratch_bytes_g2(n, pre) : msm_scratch_bytes_g1(n, pre);
     rc = t.arena.ensure(need, s);
     if (rc) return rc;
     char *scratch = t.arena.alloc<char>(need);
-    return G2 ? msm_run_g2(bases_dev, scalars_dev, n, out_jac_dev, scratch, t.err_flag, s)
-              : msm_run_g1(bases_dev, scalars_dev, n, out_jac_dev, scratch, t.err_flag, s);
+    return G2 ? msm_run_g2(bases_dev, scalars_dev, n, out_jac_dev, scratch, t.err_flag, s, pre)
+              : msm_run_g1(bases_dev, scalars_dev, n, out_jac_dev, scratch, t.err_flag, s, pre);
 }
 
 template <bool G2> static int32_t bases_upload(const uint8_t *affine, size_t n, uint64_t *handle) {
@@ -213,8 +225,28 @@ int32_t dg_bases_free(uint64_t handle) {
 
 int32_t dg_msm_g1(uint64_t h, const uint8_t *bases, const uint8_t *scalars, size_t n, uint8_t *out) { return msm_host<false>(h, bases, scalars, n, out); }
 int32_t dg_msm_g2(uint64_t h, const uint8_t *bases, const uint8_t *scalars, size_t n, uint8_t *out) { return msm_host<true>(h, bases, scalars, n, out); }
-int32_t dg_msm_g1_device(const void *b, const void *s, size_t n, void *o, void *st) { return msm_device<false>(b, s, n, o, st); }
-int32_t dg_msm_g2_device(const void *b, const void *s, size_t n, void *o, void *st) { return msm_device<true>(b, s, n, o, st); }
+int32_t dg_msm_g1_device(const void *b, const void *s, size_t n, void *o, void *st) { return msm_device<false>(0, b, s, n, o, st); }
+int32_t dg_msm_g2_device(const void *b, const void *s, size_t n, void *o, void *st) { return msm_device<true>(0, b, s, n, o, st); }
+int32_t dg_msm_g1_handle_device(uint64_t h, const void *s, size_t n, void *o, void *st) {
+    if (!h) return fail(DG_ERR_BAD_ARG, "msm_handle_device: null handle");
+    return msm_device<false>(h, nullptr, s, n, o, st);
+}
+int32_t dg_msm_g2_handle_device(uint64_t h, const void *s, size_t n, void *o, void *st) {
+    if (!h) return fail(DG_ERR_BAD_ARG, "msm_handle_device: null handle");
+    return msm_device<true>(h, nullptr, s, n, o, st);
+}
+int32_t dg_bases_precompute(uint64_t handle, int32_t c) {
+    int32_t rc = check_init();
+    if (rc) return rc;
+    std::lock_guard<std::mutex> lk(ctx().mu);
+    auto it = ctx().handles.find(handle);
+    if (it == ctx().handles.end() || (it->second.kind != HandleRec::BASES_G1 && it->second.kind != HandleRec::BASES_G2))
+        return fail(DG_ERR_BAD_ARG, "bases_precompute: bad handle");
+    if (c == 0) c = it->second.n >= (1u << 18) ? 20 : 16;
+    DG_CUDA(cudaDeviceSynchronize());
+    return it->second.kind == HandleRec::BASES_G2 ? bases_precompute_g2(it->second, c, tls().stream)
+                                                  : bases_precompute_g1(it->second, c, tls().stream);
+}
 int32_t dg_prof_enable(int32_t on) {
     ctx().prof_enabled.store(on ? 1 : 0);
     return DG_OK;

@@ -17,7 +17,7 @@ struct HandleRec {
     enum Kind { BASES_G1, BASES_G2, TABLE_G1, TABLE_G2 } kind;
     void *dev = nullptr;
     size_t n = 0;            // bases: point count; tables: total records
-    int window = 0, nwin = 0;
+    int window = 0, nwin = 0;   // tables: window geometry; bases: precompute window / rows (0 = plain)
 };
 
 struct Context {
@@ -83,11 +83,16 @@ int32_t check_init();
 static inline unsigned div_up(size_t a, size_t b) { return (unsigned)((a + b - 1) / b); }
 
 // ---- internal entry points implemented per translation unit (device pointers, async) ----------
-size_t msm_scratch_bytes_g1(size_t n);
-size_t msm_scratch_bytes_g2(size_t n);
+// Precomputed-bases descriptor: c = 0 means plain bases; otherwise the table holds ceil(256/c)
+// rows of row_stride affine points, row k = 2^(c*k) * P_i (dg_bases_precompute).
+struct MsmPre { int c; uint32_t row_stride; };
+size_t msm_scratch_bytes_g1(size_t n, MsmPre pre);
+size_t msm_scratch_bytes_g2(size_t n, MsmPre pre);
 int32_t msm_run_g1(const void *bases_dev, const void *scalars_dev, size_t n, void *out_jac_dev, char *scratch,
-                   uint32_t *err_flag, cudaStream_t s);
+                   uint32_t *err_flag, cudaStream_t s, MsmPre pre);
 int32_t msm_run_g2(const void *bases_dev, const void *scalars_dev, size_t n, void *out_jac_dev, char *scratch,
-                   uint32_t *err_flag, cudaStream_t s);
+                   uint32_t *err_flag, cudaStream_t s, MsmPre pre);
+int32_t bases_precompute_g1(HandleRec &rec, int c, cudaStream_t s);
+int32_t bases_precompute_g2(HandleRec &rec, int c, cudaStream_t s);
 
 }  // namespace dg

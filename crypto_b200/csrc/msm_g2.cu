@@ -2,9 +2,9 @@
 // legogroth16/src/prover.rs:344 b_g2_query).
 #include "msm_host.cuh"
 namespace dg {
-size_t msm_scratch_bytes_g2(size_t n) { return msm_layout<Fp2>(n).total; }
+size_t msm_scratch_bytes_g2(size_t n, MsmPre pre) { return msm_layout<Fp2>(n, pre).total; }
 int32_t msm_run_g2(const void *bases_dev, const void *scalars_dev, size_t n, void *out_jac_dev, char *scratch,
-                   uint32_t *err_flag, cudaStream_t s) {
-    return msm_run<Fp2>(bases_dev, scalars_dev, n, out_jac_dev, scratch, err_flag, s);
+                   uint32_t *err_flag, cudaStream_t s, MsmPre pre) {
+    return msm_run<Fp2>(bases_dev, scalars_dev, n, out_jac_dev, scratch, err_flag, s, pre);
 }
 }  // namespace dg

@@ -11,8 +11,8 @@ static inline int ceil_log2_sz(size_t n) { int l = 0; while (((size_t)1 << l) < 
 // Window bits: about log2(n) - 4 so that an average bucket receives ~32 points per window,
 // which keeps the bucket reduction (2 * 2^(c-1) full additions per window) near 10 % of the
 // accumulation work.  nwin * c >= 256 so the top signed digit cannot overflow.
-static inline MsmGeom msm_geometry(size_t n) {
-    int c = ctx().msm_window_override.load();
+static inline MsmGeom msm_geometry(size_t n, MsmPre pre) {
+    int c = pre.c ? pre.c : ctx().msm_window_override.load();
     if (c <= 0) {
         c = ceil_log2_sz(n ? n : 1) - 4;
         if (c < 4) c = 4;
@@ -21,9 +21,11 @@ static inline MsmGeom msm_geometry(size_t n) {
     }
     MsmGeom g;
     g.c = c;
-    g.nwin = (256 + c - 1) / c;
+    g.ndig = (256 + c - 1) / c;
+    g.nwin = pre.c ? 1 : g.ndig;
     g.nbw = 1u << (c - 1);
     g.nb = g.nbw * (uint32_t)g.nwin;
+    g.row_stride = pre.c ? pre.row_stride : 0;
     return g;
 }
 
@@ -33,10 +35,10 @@ struct MsmLayout {
     size_t o_hist, o_off, o_cursor, o_bsums, o_entries, o_buckets, o_head, o_tail, o_long, o_red[4], total;
 };
 
-template <class F> static inline MsmLayout msm_layout(size_t n) {
+template <class F> static inline MsmLayout msm_layout(size_t n, MsmPre pre) {
     MsmLayout m;
-    m.g = msm_geometry(n);
-    size_t max_entries = n * (size_t)m.g.nwin;
+    m.g = msm_geometry(n, pre);
+    size_t max_entries = n * (size_t)m.g.ndig;
     size_t threads_target = (size_t)ctx().sm_count * 384 * 4;
     size_t L = (max_entries + threads_target - 1) / threads_target;
     if (L < 8) L = 8;
@@ -68,13 +70,15 @@ template <class F> __global__ void k_set_jac_inf(Jac<F> *out) {
 
 template <class F>
 static int32_t msm_run(const void *bases_dev, const void *scalars_dev, size_t n, void *out_jac_dev, char *scratch,
-                       uint32_t *err_flag, cudaStream_t s) {
+                       uint32_t *err_flag, cudaStream_t s, MsmPre pre) {
     if (n == 0) {
         DG_LAUNCH(k_set_jac_inf<F>, 1, 32, 0, s, (Jac<F> *)out_jac_dev);
         return DG_OK;
     }
     if (n >= (1ull << 31)) return fail(DG_ERR_BAD_ARG, "msm: n must be < 2^31");
-    MsmLayout m = msm_layout<F>(n);
+    if (pre.c && (uint64_t)pre.row_stride * ((256 + pre.c - 1) / pre.c) >= (1ull << 31))
+        return fail(DG_ERR_BAD_ARG, "msm: precomputed table too large for 31-bit point indices");
+    MsmLayout m = msm_layout<F>(n, pre);
     const MsmGeom g = m.g;
     uint32_t *hist = (uint32_t *)(scratch + m.o_hist), *off = (uint32_t *)(scratch + m.o_off);
     uint32_t *cursor = (uint32_t *)(scratch + m.o_cursor), *bsums = (uint32_t *)(scratch + m.o_bsums);

@@ -23,9 +23,11 @@ namespace dg {
 
 struct MsmGeom {
     int c;            // window bits
-    int nwin;         // number of windows, nwin * c >= 256 so the top signed digit never overflows
-    uint32_t nbw;     // buckets per window = 2^(c-1)
+    int ndig;         // signed digits per scalar, ndig * c >= 256 so the top digit never overflows
+    int nwin;         // bucket sets: ndig, or 1 when the bases carry precomputed 2^(c*k) multiples
+    uint32_t nbw;     // buckets per set = 2^(c-1)
     uint32_t nb;      // total buckets = nwin * nbw
+    uint32_t row_stride;   // precomputed bases: row k (= 2^(c*k) * P_i) starts at k * row_stride; 0 = plain bases
 };
 
 // ---------------------------------------------------------------- digits / counting sort -----
@@ -40,7 +42,7 @@ __global__ void __launch_bounds__(256) k_digits(const uint32_t *__restrict__ sca
     uint32_t s[9] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w, 0};
     const uint32_t mask = (1u << g.c) - 1, half = 1u << (g.c - 1);
     uint32_t carry = 0;
-    for (int w = 0; w < g.nwin; w++) {
+    for (int w = 0; w < g.ndig; w++) {
         int bit = w * g.c;
         uint32_t raw = 0;
         if (bit < 256) {
@@ -53,12 +55,14 @@ __global__ void __launch_bounds__(256) k_digits(const uint32_t *__restrict__ sca
         carry = neg ? 1u : 0u;
         uint32_t mag = neg ? (1u << g.c) - d : d;
         if (mag != 0) {
-            uint32_t bucket = w * g.nbw + mag - 1;
+            // precomputed rows fold every digit position into ONE bucket set: digit w of scalar i
+            // selects the point 2^(c*w) * P_i stored at w * row_stride + i
+            uint32_t bucket = (g.row_stride ? 0u : w * g.nbw) + mag - 1;
             if (PASS == 0) {
                 atomicAdd(&counters[bucket], 1u);
             } else {
                 uint32_t pos = atomicAdd(&counters[bucket], 1u);
-                entries[pos] = i | (neg ? 0x80000000u : 0u);
+                entries[pos] = (i + (uint32_t)w * g.row_stride) | (neg ? 0x80000000u : 0u);
             }
         }
     }
@@ -139,7 +143,7 @@ static __global__ void __launch_bounds__(1024) k_scan_add(uint32_t *__restrict__
 //   first run of the chunk  -> head[t]       last run (if not also first) -> tail[t]
 //   runs strictly inside    -> buckets[b] directly (nobody else touches that bucket)
 template <class F>
-__global__ void __launch_bounds__(128, 3) k_accumulate(const Affine<F> *__restrict__ bases, const uint32_t *__restrict__ entries,
+__global__ void __launch_bounds__(128, 4) k_accumulate(const Affine<F> *__restrict__ bases, const uint32_t *__restrict__ entries,
                                                        const uint32_t *__restrict__ off, uint32_t nb, uint32_t L,
                                                        XYZZ<F> *__restrict__ buckets, XYZZ<F> *__restrict__ head,
                                                        XYZZ<F> *__restrict__ tail) {

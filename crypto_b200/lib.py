@@ -16,7 +16,8 @@ G1_AFF, G1_JAC, G2_AFF, G2_JAC, FP12, SCALAR = 96, 144, 192, 288, 576, 32
 # every symbol include/dockgpu.h declares (checked by tests/test_abi.py without a GPU)
 EXPORTS = [
     'dg_init', 'dg_shutdown', 'dg_last_error', 'dg_launch_count', 'dg_sync',
-    'dg_bases_upload_g1', 'dg_bases_upload_g2', 'dg_bases_free',
+    'dg_bases_upload_g1', 'dg_bases_upload_g2', 'dg_bases_free', 'dg_bases_precompute',
+    'dg_msm_g1_handle_device', 'dg_msm_g2_handle_device',
     'dg_msm_g1', 'dg_msm_g2', 'dg_msm_g1_device', 'dg_msm_g2_device', 'dg_msm_set_window',
     'dg_fixed_base_table_g1', 'dg_fixed_base_table_g2', 'dg_fixed_base_table_info',
     'dg_fixed_base_table_download', 'dg_fixed_base_table_free',
@@ -107,10 +108,22 @@ class Bases:
         _check(fn(ap, C.c_size_t(self.n), C.byref(h)))
         self.handle = h.value
 
+    def precompute(self, window_bits=0):
+        """Build the 2^(c*k) multiples table on the device (dg_bases_precompute)."""
+        _check(load().dg_bases_precompute(C.c_uint64(self.handle), C.c_int32(window_bits)))
+        return self
+
     def free(self):
         if self.handle:
             _check(load().dg_bases_free(C.c_uint64(self.handle)))
             self.handle = 0
+
+
+def msm_handle_device(bases, scalars_ptr, n, out_ptr, stream=0):
+    """Resident bases (Bases handle), scalars/output device pointers; no copies, no sync."""
+    lib = init()
+    fn = lib.dg_msm_g2_handle_device if bases.g2 else lib.dg_msm_g1_handle_device
+    _check(fn(C.c_uint64(bases.handle), C.c_void_p(scalars_ptr), C.c_size_t(n), C.c_void_p(out_ptr), C.c_void_p(stream)))
 
 
 def msm(bases, scalars, g2=False, n=None):

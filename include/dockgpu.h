@@ -64,6 +64,12 @@ int32_t dg_sync(void);
 int32_t dg_bases_upload_g1(const uint8_t *affine, size_t n, uint64_t *handle);
 int32_t dg_bases_upload_g2(const uint8_t *affine, size_t n, uint64_t *handle);
 int32_t dg_bases_free(uint64_t handle);
+/* Optional, for bases that are reused across many MSMs: replaces the resident points by the table
+ * { 2^(c*k) * P_i : k < ceil(256/c) } (ceil(256/c) x the memory, built once on the device).  MSMs
+ * through this handle then fold every digit position into ONE bucket set: no window-combination
+ * doublings and ceil(256/c) x fewer buckets to reduce.  c = 0 picks a default (20 for n >= 2^18).
+ * Results are identical group elements. */
+int32_t dg_bases_precompute(uint64_t handle, int32_t window_bits);
 
 /* ---- variable-base MSM ---------------------------------------------------------------------
  * ark_ec::VariableBaseMSM::msm_bigint(bases, bigints) for G1Projective / G2Projective
@@ -79,6 +85,9 @@ int32_t dg_msm_g2(uint64_t bases_handle, const uint8_t *bases, const uint8_t *sc
 /* device-pointer variants; out_jac_dev is device memory (144 / 288 B) */
 int32_t dg_msm_g1_device(const void *bases_dev, const void *scalars_dev, size_t n, void *out_jac_dev, void *stream);
 int32_t dg_msm_g2_device(const void *bases_dev, const void *scalars_dev, size_t n, void *out_jac_dev, void *stream);
+/* resident (optionally precomputed) bases behind a handle, scalars and output in device memory */
+int32_t dg_msm_g1_handle_device(uint64_t bases_handle, const void *scalars_dev, size_t n, void *out_jac_dev, void *stream);
+int32_t dg_msm_g2_handle_device(uint64_t bases_handle, const void *scalars_dev, size_t n, void *out_jac_dev, void *stream);
 /* Overrides the automatic window size (0 restores it); for tuning and tests. */
 int32_t dg_msm_set_window(int32_t c);
 

@@ -291,3 +291,36 @@ def test_many_pairs_tree_product(dg, cref):
     ps, _ = h.g1_bases(k, 120)
     qs, _ = h.g2_bases(k, 121)
     assert bytes(dg.multi_miller_loop(ps, qs)) == bytes(cref.multi_miller_loop(ps, qs))
+
+
+# ------------------------------------------------------------------ precomputed bases ----------
+@pytest.mark.parametrize('c', [8, 13, 16, 20])
+def test_msm_precomputed_bases(dg, cref, c):
+    """dg_bases_precompute folds all digit positions into one bucket set; same group element."""
+    n = 3000
+    bases, ks = h.g1_bases(n, 300 + c)
+    bases = bases.copy(); bases[96 * 7:96 * 8] = 0           # an identity base must stay harmless
+    ss = h.rand_scalars(n, 400 + c).copy()
+    ss[:32] = 0
+    ss[32:64] = np.frombuffer((o.R - 1).to_bytes(32, 'little'), np.uint8)
+    hb = dg.Bases(bases).precompute(c)
+    try:
+        exp = h.affine_g1(cref.msm_g1(bases, ss))
+        assert h.affine_g1(dg.msm(hb, ss)) == exp
+        # prefix use of a precomputed table
+        assert h.affine_g1(dg.msm(hb, ss[:32 * 1000])) == h.affine_g1(cref.msm_g1(bases, ss[:32 * 1000], 1000))
+        with pytest.raises(dg.DockGpuError):
+            hb.precompute(c)                                   # already precomputed
+    finally:
+        hb.free()
+
+
+def test_msm_precomputed_g2_and_default_window(dg, cref):
+    n = 600
+    bases, ks = h.g2_bases(n, 501)
+    ss = h.rand_scalars(n, 502)
+    hb = dg.Bases(bases, g2=True).precompute()
+    try:
+        assert h.affine_g2(dg.msm(hb, ss, g2=True)) == h.known_dlog_msm_g2(ks, ss)
+    finally:
+        hb.free()
