@@ -143,7 +143,7 @@ static __global__ void __launch_bounds__(1024) k_scan_add(uint32_t *__restrict__
 //   first run of the chunk  -> head[t]       last run (if not also first) -> tail[t]
 //   runs strictly inside    -> buckets[b] directly (nobody else touches that bucket)
 template <class F>
-__global__ void __launch_bounds__(128, 4) k_accumulate(const Affine<F> *__restrict__ bases, const uint32_t *__restrict__ entries,
+__global__ void __launch_bounds__(128, (sizeof(F) > 48 ? 2 : 3)) k_accumulate(const Affine<F> *__restrict__ bases, const uint32_t *__restrict__ entries,
                                                        const uint32_t *__restrict__ off, uint32_t nb, uint32_t L,
                                                        XYZZ<F> *__restrict__ buckets, XYZZ<F> *__restrict__ head,
                                                        XYZZ<F> *__restrict__ tail) {

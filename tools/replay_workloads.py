@@ -1,0 +1,168 @@
+"""Replays the L0 call sequences of BASELINE.json configs 3 and 4 through the
+C ABI with synthetic inputs of the same shapes, checks every result (known-dlog identity / oracle)
+and times the GPU next to the CPU oracle.  Writes one JSON object (stdout or --out FILE).
+
+  config 3  legogroth16::create_random_proof, D = 2^18: 4 G1 MSMs of ~2^18 terms over the
+            proving-key queries + 1 G2 MSM (b_g2_query) + a small gamma_abc MSM
+            (legogroth16/src/prover.rs:286,299,326,333,344,361)
+  config 4  bbs_plus SignatureG1::new / PoK with 10 000 messages (MSMs of 10 001 terms,
+            bbs_plus/src/setup.rs:145, proof.rs:187,241), verification 2-pair product check
+            (proof.rs:494), and a vb_accumulator batch witness update for 10 000 members
+            (witness.rs:269-284: per-witness mul_bigint + WindowTable multiply + normalize_batch)
+"""
+import argparse
+import json
+import os
+import sys
+import time
+
+import numpy as np
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from oracle import cref  # noqa: E402  (checker + CPU timing only)
+from crypto_b200 import lib, msm  # noqa: E402
+
+R = 0x73EDA753299D7D483339D80809A1D80553BDA402FFFE5BFEFFFFFFFF00000001
+
+
+def ints(b):
+    return [int.from_bytes(bytes(r), 'little') for r in np.asarray(b, dtype=np.uint8).reshape(-1, 32)]
+
+
+def sbytes(v):
+    return np.frombuffer(b''.join(int(x % R).to_bytes(32, 'little') for x in v), dtype=np.uint8)
+
+
+def dlog_total(ks, ss):
+    return sum(a * b for a, b in zip(ints(ks), ints(ss))) % R
+
+
+def timeit(fn, reps=3):
+    fn()
+    best = 1e9
+    out = None
+    for _ in range(reps):
+        t = time.perf_counter()
+        out = fn()
+        best = min(best, time.perf_counter() - t)
+    return best, out
+
+
+def config3(logd, with_cpu):
+    n = 1 << logd
+    res = {'D': n, 'msms': []}
+    total_gpu = total_cpu = 0.0
+    for name, seed, g2 in (('h_query x h', 1, False), ('l_query x witness', 2, False), ('a_query', 3, False),
+                           ('b_g1_query', 4, False), ('b_g2_query', 5, True)):
+        ks = cref.random_scalars(n, 1000 + seed)
+        ss = cref.random_scalars(n, 2000 + seed).copy()
+        sv = ss.reshape(n, 32)
+        # real witnesses are full of 0/1 and small values (SURVEY 7 'hard parts'): make 30% of them so
+        sv[: n // 10] = 0
+        sv[n // 10: n // 5] = 0
+        sv[n // 10: n // 5, 0] = 1
+        sv[n // 5: 3 * n // 10, 2:] = 0
+        bases = cref.g2_generator_muls(ks) if g2 else cref.g1_generator_muls(ks)
+        hb = lib.Bases(bases, g2=g2).precompute()
+        dt, out = timeit(lambda: lib.msm(hb, ss, g2=g2))
+        hb.free()
+        tot = dlog_total(ks, ss)
+        if g2:
+            ok = bytes(cref.normalize_batch_g2(out)) == bytes(cref.g2_generator_muls(sbytes([tot])))
+        else:
+            ok = bytes(cref.normalize_batch_g1(out)) == bytes(cref.g1_generator_muls(sbytes([tot])))
+        ent = {'name': name, 'group': 'G2' if g2 else 'G1', 'terms': n, 'gpu_ms': dt * 1e3, 'ok': ok}
+        total_gpu += dt
+        if with_cpu:
+            t = time.perf_counter()
+            (cref.msm_g2 if g2 else cref.msm_g1)(bases, ss)
+            ent['cpu_ms'] = (time.perf_counter() - t) * 1e3
+            total_cpu += ent['cpu_ms'] / 1e3
+        res['msms'].append(ent)
+        print('  ', ent, flush=True)
+    res['gpu_ms_total_msm'] = total_gpu * 1e3
+    if with_cpu:
+        res['cpu_ms_total_msm'] = total_cpu * 1e3
+    return res
+
+
+def config4(nmsg, with_cpu):
+    res = {'messages': nmsg}
+    hs, hk = None, None
+    ks = cref.random_scalars(nmsg + 1, 31)
+    hs = cref.g1_generator_muls(ks)
+    ss = cref.random_scalars(nmsg + 1, 32)
+    hb = lib.Bases(hs)
+    dt, out = timeit(lambda: lib.msm(hb, ss))
+    ok = bytes(cref.normalize_batch_g1(out)) == bytes(cref.g1_generator_muls(sbytes([dlog_total(ks, ss)])))
+    res['sign_msm'] = {'terms': nmsg + 1, 'gpu_ms': dt * 1e3, 'ok': ok}
+    if with_cpu:
+        t = time.perf_counter(); cref.msm_g1(hs, ss); res['sign_msm']['cpu_ms'] = (time.perf_counter() - t) * 1e3
+    hb.free()
+    # verification-shaped 2-pair product check  e(A, pk + e g2) * e(-b, g2) == 1
+    b_aff = bytes(cref.normalize_batch_g1(out))
+    e, x = 0x2222, 0x3333
+    A = bytes(cref.normalize_batch_g1(cref.batch_mul_g1(np.frombuffer(b_aff, np.uint8), sbytes([pow(e + x, -1, R)]))))
+    nb = bytes(cref.normalize_batch_g1(cref.batch_mul_g1(np.frombuffer(b_aff, np.uint8), sbytes([R - 1]))))
+    g2 = bytes(cref.g2_generator_muls(sbytes([1])))
+    pk = bytes(cref.g2_generator_muls(sbytes([x + e])))
+    dt, r = timeit(lambda: lib.multi_pairing_is_one(A + nb, pk + g2))
+    res['verify_2pair_check'] = {'gpu_ms': dt * 1e3, 'ok': bool(r)}
+    if with_cpu:
+        t = time.perf_counter(); cref.multi_pairing(A + nb, pk + g2); res['verify_2pair_check']['cpu_ms'] = (time.perf_counter() - t) * 1e3
+    # many pairs as the lazy RandomizedPairingChecker produces them
+    k = 256
+    ps = cref.g1_generator_muls(cref.random_scalars(k, 41)); qs = cref.g2_generator_muls(cref.random_scalars(k, 42))
+    dt, ml = timeit(lambda: lib.multi_pairing(ps, qs))
+    ok = bytes(ml) == bytes(cref.multi_pairing(ps, qs))
+    res['multi_pairing_256'] = {'pairs': k, 'gpu_ms': dt * 1e3, 'ok': ok}
+    if with_cpu:
+        t = time.perf_counter(); cref.multi_pairing(ps, qs); res['multi_pairing_256']['cpu_ms'] = (time.perf_counter() - t) * 1e3
+    # accumulator batch witness update
+    m = nmsg
+    wits = cref.g1_generator_muls(cref.random_scalars(m, 51))
+    v = cref.g1_generator_muls(cref.random_scalars(1, 52))
+    sa, sb = cref.random_scalars(m, 53), cref.random_scalars(m, 54)
+
+    def gpu_update():
+        t = lib.FixedBaseTable(v, m)
+        o = lib.batch_mul_add_fixed_g1(wits, sa, t, sb)
+        t.free()
+        return o
+    dt, out = timeit(gpu_update)
+    res['witness_update'] = {'witnesses': m, 'gpu_ms': dt * 1e3}
+    t = time.perf_counter()
+    left = cref.batch_mul_g1(wits, sa)
+    right, _, _ = cref.fixed_base_mul_many_g1(v, m, sb)
+    cpu_s = time.perf_counter() - t
+    # check the first 16 against the oracle sum
+    from oracle import bls12_381 as o
+    la = bytes(cref.normalize_batch_g1(left[:144 * 16])); ra = bytes(cref.normalize_batch_g1(right[:144 * 16]))
+    exp = b''.join(o.g1_to_bytes(o.E1.add(o.g1_from_bytes(la[96 * i:96 * i + 96]), o.g1_from_bytes(ra[96 * i:96 * i + 96]))) for i in range(16))
+    res['witness_update']['ok'] = bytes(out[:96 * 16]) == exp
+    res['witness_update']['cpu_ms'] = cpu_s * 1e3
+    return res
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--logd', type=int, default=18)
+    ap.add_argument('--messages', type=int, default=10000)
+    ap.add_argument('--no-cpu', action='store_true')
+    ap.add_argument('--out', default='')
+    a = ap.parse_args()
+    lib.init()
+    out = {'host_cores': len(os.sched_getaffinity(0)), 'note': 'gpu_ms = host C-ABI call incl. H2D of scalars and D2H of the result; '
+           'cpu_ms = oracle C restatement of the arkworks algorithm on the host cores'}
+    print('config 3', flush=True)
+    out['config3_legogroth16_prover_shape'] = config3(a.logd, not a.no_cpu)
+    print('config 4', flush=True)
+    out['config4_bbs_plus_and_accumulator_shape'] = config4(a.messages, not a.no_cpu)
+    s = json.dumps(out, indent=1)
+    if a.out:
+        open(a.out, 'w').write(s)
+    print(s)
+
+
+if __name__ == '__main__':
+    main()
