@@ -48,11 +48,29 @@ __device__ __forceinline__ void fp2_from_parts(Fp *d, const Fp *p) {
 }
 
 struct Engine {
-    Fp prod[108];      // product scratch
-    Fp tmp[16];        // linear-stage scratch
+    Fp prod[108];      // product scratch (3 Karatsuba parts of up to 36 Fp2 products)
+    Fp q[72];          // the 36 Fp2 products after recombination / xi-twist
+    Fp tmp[24];        // linear-stage scratch
 };
 
+// a / 2 mod p without a multiplication: make it even by adding p, then shift right
+__device__ __forceinline__ Fp fp_half(const Fp &a) {
+    uint32_t odd = 0u - (a.l[0] & 1u);
+    Fp t;
+    asm volatile("add.cc.u32 %0, %1, %2;" : "=r"(t.l[0]) : "r"(a.l[0]), "r"(odd & fp_p_limb(0)));
+#pragma unroll
+    for (int i = 1; i < 12; i++) asm volatile("addc.cc.u32 %0, %1, %2;" : "=r"(t.l[i]) : "r"(a.l[i]), "r"(odd & fp_p_limb(i)));
+    Fp r;
+#pragma unroll
+    for (int i = 0; i < 11; i++) r.l[i] = (t.l[i] >> 1) | (t.l[i + 1] << 31);
+    r.l[11] = t.l[11] >> 1;                 // a + p < 2^382: no carry out of limb 11
+    return r;
+}
+
 // C = A * B (C may alias A or B).  All PAIR_THREADS threads must call.
+//   phase 1: 108 lanes, one Fp multiplication each (36 Fp2 products x 3 Karatsuba parts)
+//   phase 2:  36 lanes recombine their Fp2 product and apply the w^6 = xi twist when i + j >= 6
+//   phase 3:  12 lanes (degree k, component) add the six products of their column
 __device__ void f12_mul(Engine &e, F12 *C, const F12 *A, const F12 *B) {
     int tid = threadIdx.x;
     if (tid < 108) {
@@ -60,28 +78,28 @@ __device__ void f12_mul(Engine &e, F12 *C, const F12 *A, const F12 *B) {
         e.prod[tid] = fp2_part(part, &A->c[widx(i)], &B->c[widx(j)]);
     }
     __syncthreads();
+    if (tid < 36) {
+        int i = tid / 6, j = tid - i * 6;
+        const Fp *p = &e.prod[tid * 3];
+        Fp c0 = fp_sub(p[0], p[1]);
+        Fp c1 = fp_sub(fp_sub(p[2], p[0]), p[1]);
+        if (i + j >= 6) {                         // times xi = 1 + u
+            Fp t0 = fp_sub(c0, c1), t1 = fp_add(c0, c1);
+            c0 = t0; c1 = t1;
+        }
+        e.q[2 * tid] = c0;
+        e.q[2 * tid + 1] = c1;
+    }
+    __syncthreads();
     if (tid < 12) {
         int k = tid >> 1, comp = tid & 1;
-        // T* over i+j = k, U* over i+j = k+6 (w^6 = xi = 1+u)
-        Fp T0 = fp_zero(), T1 = fp_zero(), T2 = fp_zero(), U0 = fp_zero(), U1 = fp_zero(), U2 = fp_zero();
+        Fp acc = fp_zero();
+#pragma unroll
         for (int i = 0; i < 6; i++) {
-            int j = k - i;
-            if (j >= 0 && j < 6) {
-                const Fp *p = &e.prod[(i * 6 + j) * 3];
-                if (comp == 0) { T0 = fp_add(T0, p[0]); T1 = fp_add(T1, p[1]); }
-                else { T0 = fp_add(T0, fp_add(p[0], p[1])); T2 = fp_add(T2, p[2]); }
-            }
-            j = k + 6 - i;
-            if (j >= 0 && j < 6) {
-                const Fp *p = &e.prod[(i * 6 + j) * 3];
-                if (comp == 0) { U0 = fp_add(U0, p[0]); U2 = fp_add(U2, p[2]); }
-                else { U1 = fp_add(U1, p[1]); U2 = fp_add(U2, p[2]); }
-            }
+            int j = k - i; if (j < 0) j += 6;
+            acc = fp_add(acc, e.q[2 * (i * 6 + j) + comp]);
         }
-        Fp r;
-        if (comp == 0) r = fp_sub(fp_add(fp_sub(T0, T1), fp_dbl(U0)), U2);      // T0 - T1 + 2 U0 - U2
-        else r = fp_sub(fp_add(fp_sub(T2, T0), U2), fp_dbl(U1));               // T2 - (T0+T1) + U2 - 2 U1
-        C->c[widx(k) + comp] = r;
+        C->c[widx(k) + comp] = acc;
     }
     __syncthreads();
 }
@@ -214,54 +232,61 @@ struct MillerState {
 __device__ __forceinline__ void fp2s_add(Fp *d, const Fp *a, const Fp *b) { Fp x = fp_add(a[0], b[0]), y = fp_add(a[1], b[1]); d[0] = x; d[1] = y; }
 __device__ __forceinline__ void fp2s_sub(Fp *d, const Fp *a, const Fp *b) { Fp x = fp_sub(a[0], b[0]), y = fp_sub(a[1], b[1]); d[0] = x; d[1] = y; }
 __device__ __forceinline__ void fp2s_neg(Fp *d, const Fp *a) { Fp x = fp_neg(a[0]), y = fp_neg(a[1]); d[0] = x; d[1] = y; }
-__device__ __forceinline__ void fp2s_half(Fp *d, const Fp *a, const Fp &two_inv) { Fp x = fp_mul(a[0], two_inv), y = fp_mul(a[1], two_inv); d[0] = x; d[1] = y; }
+__device__ __forceinline__ void fp2s_half(Fp *d, const Fp *a) { Fp x = fp_half(a[0]), y = fp_half(a[1]); d[0] = x; d[1] = y; }
 
-// Doubling step (ark G2Prepared double_in_place), two product waves.
+// Doubling step (ark G2Prepared double_in_place): two product waves; the linear algebra between
+// them is spread over several lanes instead of one.
+//   T layout (Fp2 = 2 slots): 0 m1=rx*ry  2 b  4 c  6 j  8 s  10 e  12 f  14 a  16 g  18 h  20 b-f
 __device__ void miller_double(Engine &e, MillerState &m) {
     int tid = threadIdx.x;
-    Fp *T = e.tmp;     // T[0..1] = ry+rz
-    if (tid == 0) fp2s_add(&T[0], m.ry, m.rz);
-    __syncthreads();
+    Fp *T = e.tmp;
     // wave 1: 0: rx*ry  1: ry^2  2: rz^2  3: rx^2  4: (ry+rz)^2
     if (tid < 15) {
         int job = tid / 3, part = tid - job * 3;
+        Fp sum[2];
         const Fp *A, *B;
         switch (job) {
             case 0: A = m.rx; B = m.ry; break;
             case 1: A = m.ry; B = m.ry; break;
             case 2: A = m.rz; B = m.rz; break;
             case 3: A = m.rx; B = m.rx; break;
-            default: A = &T[0]; B = &T[0]; break;
+            default: fp2s_add(sum, m.ry, m.rz); A = sum; B = sum; break;
         }
         e.prod[tid] = fp2_part(part, A, B);
     }
     __syncthreads();
-    // linear stage: a, b, c, j, s -> e, f, g, h, i ; T layout: 2:a 4:b 6:e 8:g 10:h 12:(b-f)
-    if (tid == 0) {
-        Fp two_inv;
-#pragma unroll
-        for (int t = 0; t < 12; t++) two_inv.l[t] = DGC_TWO_INV[t];
-        Fp a[2], b[2], c[2], j[2], s[2], ee[2], f[2], g[2], h[2], i[2], t3[2];
-        fp2_from_parts(a, &e.prod[0]); fp2_from_parts(b, &e.prod[3]); fp2_from_parts(c, &e.prod[6]);
-        fp2_from_parts(j, &e.prod[9]); fp2_from_parts(s, &e.prod[12]);
-        fp2s_half(a, a, two_inv);
-        fp2s_add(t3, c, c); fp2s_add(t3, t3, c);                 // 3c
-        // e = (4+4u) * 3c = 4 * xi * 3c
+    if (tid < 5) fp2_from_parts(&T[2 * tid], &e.prod[3 * tid]);          // m1, b, c, j, s
+    __syncthreads();
+    if (tid == 0) {                                                        // e = (4+4u)*3c = 4*xi*3c ; f = 3e
+        Fp t3[2], ee[2], f[2];
+        fp2s_add(t3, &T[4], &T[4]); fp2s_add(t3, t3, &T[4]);
         Fp x0 = fp_sub(t3[0], t3[1]), x1 = fp_add(t3[0], t3[1]);
         ee[0] = fp_dbl(fp_dbl(x0)); ee[1] = fp_dbl(fp_dbl(x1));
-        fp2s_add(f, ee, ee); fp2s_add(f, f, ee);                 // 3e
-        fp2s_add(g, b, f); fp2s_half(g, g, two_inv);
-        fp2s_add(t3, b, c); fp2s_sub(h, s, t3);
-        fp2s_sub(i, ee, b);
-        m.co[0][0] = i[0]; m.co[0][1] = i[1];
-        fp2s_add(t3, j, j); fp2s_add(t3, t3, j);
-        m.co[1][0] = t3[0]; m.co[1][1] = t3[1];
+        fp2s_add(f, ee, ee); fp2s_add(f, f, ee);
+        T[10] = ee[0]; T[11] = ee[1]; T[12] = f[0]; T[13] = f[1];
+    } else if (tid == 1) {                                                 // h = s - (b + c) ; co2 = -h
+        Fp t3[2], h[2];
+        fp2s_add(t3, &T[2], &T[4]); fp2s_sub(h, &T[8], t3);
+        T[18] = h[0]; T[19] = h[1];
         fp2s_neg(t3, h);
         m.co[2][0] = t3[0]; m.co[2][1] = t3[1];
-        T[2] = a[0]; T[3] = a[1]; T[4] = b[0]; T[5] = b[1]; T[6] = ee[0]; T[7] = ee[1];
-        T[8] = g[0]; T[9] = g[1]; T[10] = h[0]; T[11] = h[1];
-        fp2s_sub(t3, b, f);
-        T[12] = t3[0]; T[13] = t3[1];
+    } else if (tid == 2) {                                                 // co1 = 3j
+        Fp t3[2];
+        fp2s_add(t3, &T[6], &T[6]); fp2s_add(t3, t3, &T[6]);
+        m.co[1][0] = t3[0]; m.co[1][1] = t3[1];
+    } else if (tid == 3) {                                                 // a = m1 / 2
+        fp2s_half(&T[14], &T[0]);
+    }
+    __syncthreads();
+    if (tid == 0) {                                                        // g = (b + f) / 2
+        Fp g[2];
+        fp2s_add(g, &T[2], &T[12]); fp2s_half(&T[16], g);
+    } else if (tid == 1) {                                                 // co0 = i = e - b
+        Fp i[2];
+        fp2s_sub(i, &T[10], &T[2]);
+        m.co[0][0] = i[0]; m.co[0][1] = i[1];
+    } else if (tid == 2) {                                                 // b - f
+        fp2s_sub(&T[20], &T[2], &T[12]);
     }
     __syncthreads();
     // wave 2: 0: a*(b-f)  1: g^2  2: e^2  3: b*h
@@ -269,19 +294,19 @@ __device__ void miller_double(Engine &e, MillerState &m) {
         int job = tid / 3, part = tid - job * 3;
         const Fp *A, *B;
         switch (job) {
-            case 0: A = &T[2]; B = &T[12]; break;
-            case 1: A = &T[8]; B = &T[8]; break;
-            case 2: A = &T[6]; B = &T[6]; break;
-            default: A = &T[4]; B = &T[10]; break;
+            case 0: A = &T[14]; B = &T[20]; break;
+            case 1: A = &T[16]; B = &T[16]; break;
+            case 2: A = &T[10]; B = &T[10]; break;
+            default: A = &T[2]; B = &T[18]; break;
         }
         e.prod[tid] = fp2_part(part, A, B);
     }
     __syncthreads();
-    if (tid == 0) {
+    if (tid == 0) fp2_from_parts(m.rx, &e.prod[0]);
+    else if (tid == 1) fp2_from_parts(m.rz, &e.prod[9]);
+    else if (tid == 2) {
         Fp g2[2], e2[2], t3[2];
-        fp2_from_parts(m.rx, &e.prod[0]);
         fp2_from_parts(g2, &e.prod[3]); fp2_from_parts(e2, &e.prod[6]);
-        fp2_from_parts(m.rz, &e.prod[9]);
         fp2s_add(t3, e2, e2); fp2s_add(t3, t3, e2);
         fp2s_sub(m.ry, g2, t3);
     }
