@@ -1,0 +1,293 @@
+// Number-theoretic transform over the BLS12-381 scalar field on sm_100a -- SURVEY.md 8f row f1,
+// the first "next" row after the MSM / pairing hot path.
+//
+// Replaces ark_poly::Radix2EvaluationDomain<Fr>::{fft_in_place, ifft_in_place} and the coset
+// variants with offset Fr::GENERATOR = 7, and the tail of
+// LibsnarkReduction::witness_map_from_matrices (legogroth16/src/r1cs_to_qap.rs:187-207):
+// 3 iFFT + 3 coset FFT + pointwise (a*b - c)/Z(7) + 1 coset iFFT at D = 2^18..2^19, whose output
+// `h` feeds the h_query MSM (legogroth16/src/prover.rs:286) without leaving the device.
+//
+// Layout: n = 2^k Fr elements, 32 B each (Montgomery limbs exactly as ark-ff stores them), natural
+// order in and out.  The whole vector (8-16 MB at 2^18-2^19) lives in L2; the transform is a
+// bit-reversal pass followed by radix-2 DIT stages grouped so that each CTA keeps a tile in shared
+// memory for up to 8 (first pass, contiguous) or 6 (later passes, strided tiles of 8 x 32 B
+// contiguous elements) stages: 3 passes over the data at 2^19.  Twiddles, coset powers and 1/n
+// come from per-size tables built once on the device (plan cache).
+#include <map>
+#include "common.cuh"
+#include "fr.cuh"
+
+namespace dg {
+
+struct NttPlan {
+    uint32_t logn = 0;
+    Fr *tw_fwd = nullptr, *tw_inv = nullptr;       // g^i, g^-i            (n/2 each)
+    Fr *scale_fwd = nullptr, *scale_inv = nullptr; // 7^i ; n^-1 * 7^-i     (n each)
+    Fr *consts = nullptr;                          // [0] n^-1  [1] 1/(7^n - 1)
+};
+static std::map<uint32_t, NttPlan> &plans() {
+    static std::map<uint32_t, NttPlan> p;
+    return p;
+}
+
+// consts layout produced by k_ntt_consts: 0 g, 1 g^-1, 2 n^-1, 3 7, 4 7^-1, 5 1/(7^n - 1)
+__device__ Fr fr_pow_limbs(const Fr &a, const uint32_t *e, int nbits) {
+    Fr acc = fr_one();
+    for (int i = nbits - 1; i >= 0; i--) {
+        acc = fr_mul(acc, acc);
+        if ((e[i >> 5] >> (i & 31)) & 1) acc = fr_mul(acc, a);
+    }
+    return acc;
+}
+__device__ Fr fr_inv(const Fr &a) {                  // a^(r-2)
+    uint32_t e[8];
+#pragma unroll
+    for (int i = 0; i < 8; i++) e[i] = fr_mod_limb(i);
+    e[0] = 0xffffffffu;                              // r - 2: r ends in ...ffffffff 00000001, the -2 borrows from limb 1
+    e[1] -= 1;
+    return fr_pow_limbs(a, e, 255);
+}
+__global__ void k_ntt_consts(uint32_t logn, Fr *c) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    Fr g = fr_const(DGC_FR_W32);
+    for (uint32_t i = logn; i < 32; i++) g = fr_mul(g, g);     // W32^(2^(32-logn))
+    Fr gen = fr_const(DGC_FR_GEN);
+    Fr nn = fr_zero();
+    nn.l[0] = 1u << logn;                                        // logn <= 28
+    nn = fr_mul(nn, fr_const(DGC_FR_R2));                        // to Montgomery form
+    uint32_t e[8] = {1u << logn, 0, 0, 0, 0, 0, 0, 0};
+    Fr z = fr_sub(fr_pow_limbs(gen, e, 32), fr_one());           // 7^n - 1
+    c[0] = g; c[1] = fr_inv(g); c[2] = fr_inv(nn); c[3] = gen; c[4] = fr_inv(gen); c[5] = fr_inv(z);
+}
+// out[i] = first * base^i for i < count (thread i: square-and-multiply over the bits of i)
+__global__ void __launch_bounds__(256) k_pow_table(const Fr *base_p, const Fr *first_p, uint32_t count, Fr *out) {
+    __shared__ Fr pw[32];
+    if (threadIdx.x == 0) {
+        Fr b = *base_p;
+        for (int k = 0; k < 32; k++) { pw[k] = b; b = fr_mul(b, b); }
+    }
+    __syncthreads();
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= count) return;
+    Fr acc = first_p ? *first_p : fr_one();
+    for (int k = 0; k < 32 && (i >> k); k++)
+        if ((i >> k) & 1) acc = fr_mul(acc, pw[k]);
+    fr_store(&out[i], acc);
+}
+
+// out[bitrev(i)] = in[i] * (scale ? scale[i] : 1)
+__global__ void __launch_bounds__(256) k_ntt_bitrev(const Fr *__restrict__ in, Fr *__restrict__ out, uint32_t logn,
+                                                    const Fr *__restrict__ scale) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (1u << logn)) return;
+    Fr v = fr_load(&in[i]);
+    if (scale) v = fr_mul(v, fr_load(&scale[i]));
+    uint32_t j = logn ? (__brev(i) >> (32 - logn)) : 0;
+    fr_store(&out[j], v);
+}
+
+// DIT stages s0+1 .. s0+S on a tile: element index = high << (s0+S) | mid << s0 | low, the CTA owns
+// all 2^S values of `mid` for one `high` and TL consecutive `low` values.
+// Stage t pairs mid with mid | 2^(t-1); twiddle exponent ((mid & (2^(t-1)-1)) << s0 | low) << (k-s0-t).
+template <int TL>
+__global__ void __launch_bounds__(256) k_ntt_stages(Fr *__restrict__ data, uint32_t logn, uint32_t s0, uint32_t S,
+                                                    const Fr *__restrict__ tw) {
+    extern __shared__ __align__(16) unsigned char dg_ntt_smem[];
+    Fr *sm = reinterpret_cast<Fr *>(dg_ntt_smem);              // [mid][l], 2^S x TL
+    const uint32_t nmid = 1u << S, low_tiles = (1u << s0) / TL;
+    const uint32_t high = blockIdx.x / low_tiles, low0 = (blockIdx.x % low_tiles) * TL;
+    const size_t base = ((size_t)high << (s0 + S)) + low0;
+    for (uint32_t e = threadIdx.x; e < nmid * TL; e += blockDim.x) {
+        uint32_t mid = e / TL, l = e % TL;
+        sm[e] = fr_load(&data[base + ((size_t)mid << s0) + l]);
+    }
+    __syncthreads();
+    const uint32_t nbf = (nmid >> 1) * TL;
+    for (uint32_t t = 1; t <= S; t++) {
+        const uint32_t half = 1u << (t - 1);
+        for (uint32_t b = threadIdx.x; b < nbf; b += blockDim.x) {
+            uint32_t pair = b / TL, l = b % TL;
+            uint32_t jlo = pair & (half - 1);
+            uint32_t mid_lo = ((pair >> (t - 1)) << t) | jlo, mid_hi = mid_lo | half;
+            uint32_t tw_idx = ((jlo << s0) | (low0 + l)) << (logn - s0 - t);
+            Fr u = sm[mid_lo * TL + l];
+            Fr v = fr_mul(sm[mid_hi * TL + l], fr_load(&tw[tw_idx]));
+            sm[mid_lo * TL + l] = fr_add(u, v);
+            sm[mid_hi * TL + l] = fr_sub(u, v);
+        }
+        __syncthreads();
+    }
+    for (uint32_t e = threadIdx.x; e < nmid * TL; e += blockDim.x) {
+        uint32_t mid = e / TL, l = e % TL;
+        fr_store(&data[base + ((size_t)mid << s0) + l], sm[e]);
+    }
+}
+
+// out[i] = in[i] * (scale ? scale[i] : 1) * (cst ? *cst : 1)
+__global__ void __launch_bounds__(256) k_ntt_finish(const Fr *__restrict__ in, Fr *__restrict__ out, uint32_t n,
+                                                    const Fr *__restrict__ scale, const Fr *__restrict__ cst) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    Fr v = fr_load(&in[i]);
+    if (scale) v = fr_mul(v, fr_load(&scale[i]));
+    if (cst) v = fr_mul(v, *cst);
+    fr_store(&out[i], v);
+}
+// ab[i] = (a[i] * b[i] - c[i]) * zinv
+__global__ void __launch_bounds__(256) k_qap_pointwise(Fr *__restrict__ a, const Fr *__restrict__ b, const Fr *__restrict__ c,
+                                                       uint32_t n, const Fr *__restrict__ zinv) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) fr_store(&a[i], fr_mul(fr_sub(fr_mul(fr_load(&a[i]), fr_load(&b[i])), fr_load(&c[i])), *zinv));
+}
+
+__global__ void __launch_bounds__(128) k_dbg_fr_op(int op, const Fr *a, const Fr *b, uint32_t n, Fr *out) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    Fr x = fr_load(&a[i]), y = fr_load(&b[i]), r;
+    switch (op) {
+        case 0: r = fr_mul(x, y); break;
+        case 1: r = fr_add(x, y); break;
+        case 2: r = fr_sub(x, y); break;
+        default: r = fr_inv(x); break;
+    }
+    fr_store(&out[i], r);
+}
+
+static int32_t get_plan(uint32_t logn, cudaStream_t s, NttPlan &out) {
+    std::lock_guard<std::mutex> lk(ctx().mu);
+    auto it = plans().find(logn);
+    if (it != plans().end()) { out = it->second; return DG_OK; }
+    NttPlan p;
+    p.logn = logn;
+    size_t n = (size_t)1 << logn, half = n > 1 ? n / 2 : 1;
+    Fr *c6 = nullptr;
+    DG_CUDA(cudaMalloc(&c6, sizeof(Fr) * 8));
+    DG_CUDA(cudaMalloc(&p.tw_fwd, sizeof(Fr) * half));
+    DG_CUDA(cudaMalloc(&p.tw_inv, sizeof(Fr) * half));
+    DG_CUDA(cudaMalloc(&p.scale_fwd, sizeof(Fr) * n));
+    DG_CUDA(cudaMalloc(&p.scale_inv, sizeof(Fr) * n));
+    DG_LAUNCH(k_ntt_consts, 1, 32, 0, s, logn, c6);
+    DG_LAUNCH(k_pow_table, div_up(half, 256), 256, 0, s, c6 + 0, (const Fr *)nullptr, (uint32_t)half, p.tw_fwd);
+    DG_LAUNCH(k_pow_table, div_up(half, 256), 256, 0, s, c6 + 1, (const Fr *)nullptr, (uint32_t)half, p.tw_inv);
+    DG_LAUNCH(k_pow_table, div_up(n, 256), 256, 0, s, c6 + 3, (const Fr *)nullptr, (uint32_t)n, p.scale_fwd);
+    DG_LAUNCH(k_pow_table, div_up(n, 256), 256, 0, s, c6 + 4, c6 + 2, (uint32_t)n, p.scale_inv);      // n^-1 * 7^-i
+    DG_CUDA(cudaStreamSynchronize(s));
+    p.consts = c6;                      // [2] = n^-1, [5] = 1/(7^n - 1)
+    plans()[logn] = p;
+    out = p;
+    return DG_OK;
+}
+
+// In-place transform of `data` (device), `tmp` is an n-element scratch buffer.
+static int32_t ntt_device(Fr *data, Fr *tmp, uint32_t logn, bool inverse, bool coset, cudaStream_t s) {
+    if (logn > 28) return fail(DG_ERR_BAD_ARG, "ntt: logn must be <= 28");
+    NttPlan p;
+    int32_t rc = get_plan(logn, s, p);
+    if (rc) return rc;
+    const uint32_t n = 1u << logn;
+    // bit-reversal (+ forward coset scaling a_i *= 7^i) into tmp, stages in place on tmp, copy / scale back
+    DG_LAUNCH(k_ntt_bitrev, div_up(n, 256), 256, 0, s, data, tmp, logn, (!inverse && coset) ? p.scale_fwd : (const Fr *)nullptr);
+    const Fr *tw = inverse ? p.tw_inv : p.tw_fwd;
+    uint32_t s0 = 0;
+    while (s0 < logn) {
+        if (s0 == 0) {
+            uint32_t S = logn < 8 ? logn : 8;
+            uint32_t threads = (1u << S) / 2 < 32 ? 32 : (1u << S) / 2;
+            DG_LAUNCH(k_ntt_stages<1>, n >> S, threads, sizeof(Fr) << S, s, tmp, logn, 0u, S, tw);
+            s0 = S;
+        } else {
+            uint32_t S = logn - s0 < 6 ? logn - s0 : 6;
+            DG_LAUNCH(k_ntt_stages<8>, n >> (S + 3), 256, (sizeof(Fr) << S) * 8, s, tmp, logn, s0, S, tw);
+            s0 += S;
+        }
+    }
+    // copy back, with a_i *= n^-1 (* 7^-i for the coset variant) on the inverse transform
+    DG_LAUNCH(k_ntt_finish, div_up(n, 256), 256, 0, s, tmp, data, n, (inverse && coset) ? p.scale_inv : (const Fr *)nullptr,
+              (inverse && !coset) ? p.consts + 2 : (const Fr *)nullptr);
+    return DG_OK;
+}
+
+static int32_t ntt_host(uint8_t *data, uint32_t logn, int32_t inverse, int32_t coset) {
+    int32_t rc = check_init();
+    if (rc) return rc;
+    if (!data) return fail(DG_ERR_BAD_ARG, "fr_ntt: null pointer");
+    if (logn > 28) return fail(DG_ERR_BAD_ARG, "fr_ntt: logn must be <= 28");
+    ThreadState &t = tls();
+    size_t n = (size_t)1 << logn;
+    rc = t.arena.ensure(2 * Arena::pad(sizeof(Fr) * n), t.stream);
+    if (rc) return rc;
+    Fr *d = t.arena.alloc<Fr>(n), *tmp = t.arena.alloc<Fr>(n);
+    DG_CUDA(cudaMemcpyAsync(d, data, sizeof(Fr) * n, cudaMemcpyHostToDevice, t.stream));
+    rc = ntt_device(d, tmp, logn, inverse != 0, coset != 0, t.stream);
+    if (rc) return rc;
+    DG_CUDA(cudaMemcpyAsync(data, d, sizeof(Fr) * n, cudaMemcpyDeviceToHost, t.stream));
+    DG_CUDA(cudaStreamSynchronize(t.stream));
+    return DG_OK;
+}
+
+}  // namespace dg
+
+using namespace dg;
+
+extern "C" {
+
+int32_t dg_fr_ntt(uint8_t *data, uint32_t logn, int32_t inverse, int32_t coset) { return ntt_host(data, logn, inverse, coset); }
+
+int32_t dg_fr_ntt_device(void *data_dev, void *tmp_dev, uint32_t logn, int32_t inverse, int32_t coset, void *stream) {
+    int32_t rc = check_init();
+    if (rc) return rc;
+    if (!data_dev || !tmp_dev) return fail(DG_ERR_BAD_ARG, "fr_ntt_device: null pointer");
+    cudaStream_t s = stream ? (cudaStream_t)stream : tls().stream;
+    return ntt_device((Fr *)data_dev, (Fr *)tmp_dev, logn, inverse != 0, coset != 0, s);
+}
+
+// test hook: out[i] = a[i] (op) b[i]  with op 0 mul, 1 add, 2 sub, 3 inverse(a)
+int32_t dg_dbg_fr_op(int32_t op, const uint8_t *a, const uint8_t *b, size_t n, uint8_t *out) {
+    int32_t rc = check_init();
+    if (rc) return rc;
+    if (!a || !b || !out || n == 0) return fail(DG_ERR_BAD_ARG, "dbg_fr_op: null pointer");
+    ThreadState &t = tls();
+    rc = t.arena.ensure(3 * Arena::pad(32 * n), t.stream);
+    if (rc) return rc;
+    Fr *d_a = t.arena.alloc<Fr>(n), *d_b = t.arena.alloc<Fr>(n), *d_o = t.arena.alloc<Fr>(n);
+    DG_CUDA(cudaMemcpyAsync(d_a, a, 32 * n, cudaMemcpyHostToDevice, t.stream));
+    DG_CUDA(cudaMemcpyAsync(d_b, b, 32 * n, cudaMemcpyHostToDevice, t.stream));
+    DG_LAUNCH(k_dbg_fr_op, div_up(n, 128), 128, 0, t.stream, op, d_a, d_b, (uint32_t)n, d_o);
+    DG_CUDA(cudaMemcpyAsync(out, d_o, 32 * n, cudaMemcpyDeviceToHost, t.stream));
+    DG_CUDA(cudaStreamSynchronize(t.stream));
+    return DG_OK;
+}
+
+// h = coset_ifft( (coset_fft(ifft a) * coset_fft(ifft b) - coset_fft(ifft c)) / (7^n - 1) )
+int32_t dg_qap_h_from_abc(const uint8_t *a, const uint8_t *b, const uint8_t *c, uint32_t logn, uint8_t *out_h) {
+    int32_t rc = check_init();
+    if (rc) return rc;
+    if (!a || !b || !c || !out_h) return fail(DG_ERR_BAD_ARG, "qap_h_from_abc: null pointer");
+    if (logn > 28) return fail(DG_ERR_BAD_ARG, "qap_h_from_abc: logn must be <= 28");
+    ThreadState &t = tls();
+    size_t n = (size_t)1 << logn;
+    rc = t.arena.ensure(4 * Arena::pad(sizeof(Fr) * n), t.stream);
+    if (rc) return rc;
+    Fr *d[3], *tmp;
+    for (int k = 0; k < 3; k++) d[k] = t.arena.alloc<Fr>(n);
+    tmp = t.arena.alloc<Fr>(n);
+    const uint8_t *src[3] = {a, b, c};
+    for (int k = 0; k < 3; k++) DG_CUDA(cudaMemcpyAsync(d[k], src[k], sizeof(Fr) * n, cudaMemcpyHostToDevice, t.stream));
+    for (int k = 0; k < 3; k++) {
+        rc = ntt_device(d[k], tmp, logn, true, false, t.stream);
+        if (rc) return rc;
+        rc = ntt_device(d[k], tmp, logn, false, true, t.stream);
+        if (rc) return rc;
+    }
+    NttPlan p;
+    rc = get_plan(logn, t.stream, p);
+    if (rc) return rc;
+    DG_LAUNCH(k_qap_pointwise, div_up(n, 256), 256, 0, t.stream, d[0], d[1], d[2], (uint32_t)n, p.consts + 5);
+    rc = ntt_device(d[0], tmp, logn, true, true, t.stream);
+    if (rc) return rc;
+    DG_CUDA(cudaMemcpyAsync(out_h, d[0], sizeof(Fr) * n, cudaMemcpyDeviceToHost, t.stream));
+    DG_CUDA(cudaStreamSynchronize(t.stream));
+    return DG_OK;
+}
+
+}  // extern "C"

@@ -27,8 +27,9 @@ EXPORTS = [
     'dg_multi_miller_loop', 'dg_final_exponentiation', 'dg_multi_pairing', 'dg_multi_pairing_is_one',
     'dg_gt_pow', 'dg_fp12_mul',
     'dg_fold_g1', 'dg_fold_g1_device', 'dg_fold_g2',
+    'dg_fr_ntt', 'dg_fr_ntt_device', 'dg_qap_h_from_abc',
     'dg_prof_enable', 'dg_prof_read_accumulate',
-    'dg_dbg_fp_op',
+    'dg_dbg_fp_op', 'dg_dbg_fr_op',
 ]
 
 
@@ -302,6 +303,27 @@ def fp12_mul(a, b):
     return o[:FP12]
 
 
+def fr_ntt(data, logn, inverse=False, coset=False):
+    """Radix2EvaluationDomain fft / ifft (+ coset) over Fr; returns a new array."""
+    lib = init()
+    a = np.array(_in(data)[0], dtype=np.uint8, copy=True)
+    _check(lib.dg_fr_ntt(C.c_void_p(a.ctypes.data), C.c_uint32(logn), C.c_int32(1 if inverse else 0), C.c_int32(1 if coset else 0)))
+    return a
+
+
+def fr_ntt_device(data_ptr, tmp_ptr, logn, inverse=False, coset=False, stream=0):
+    _check(init().dg_fr_ntt_device(C.c_void_p(data_ptr), C.c_void_p(tmp_ptr), C.c_uint32(logn), C.c_int32(1 if inverse else 0),
+                                   C.c_int32(1 if coset else 0), C.c_void_p(stream)))
+
+
+def qap_h_from_abc(a, b, c, logn):
+    lib = init()
+    x, xp = _in(a); y, yp = _in(b); z, zp = _in(c)
+    o, op = _out(32 << logn)
+    _check(lib.dg_qap_h_from_abc(xp, yp, zp, C.c_uint32(logn), op))
+    return o[:32 << logn]
+
+
 def dbg_fp_op(op_code, a, b):
     lib = init()
     x, xp = _in(a); y, yp = _in(b)
@@ -309,3 +331,12 @@ def dbg_fp_op(op_code, a, b):
     o, op = _out(48 * n)
     _check(lib.dg_dbg_fp_op(C.c_int32(op_code), xp, yp, C.c_size_t(n), op))
     return o[:48 * n]
+
+
+def dbg_fr_op(op_code, a, b):
+    lib = init()
+    x, xp = _in(a); y, yp = _in(b)
+    n = x.size // 32
+    o, op = _out(32 * n)
+    _check(lib.dg_dbg_fr_op(C.c_int32(op_code), xp, yp, C.c_size_t(n), op))
+    return o[:32 * n]

@@ -144,6 +144,19 @@ int32_t dg_fold_g1(const uint8_t *jac_points, size_t k, uint8_t *out_jac);
 int32_t dg_fold_g1_device(const void *jac_points_dev, size_t k, void *out_jac_dev, void *stream);
 int32_t dg_fold_g2(const uint8_t *jac_points, size_t k, uint8_t *out_jac);
 
+/* ---- NTT over Fr ("next" row f1 of SURVEY.md 8f) ---------------------------------------------------
+ * ark_poly::Radix2EvaluationDomain<Fr> of size 2^logn: fft_in_place / ifft_in_place (inverse = 1) and
+ * the coset variants (coset = 1) with offset Fr::GENERATOR = 7, as legogroth16's witness map uses
+ * them (legogroth16/src/r1cs_to_qap.rs:187-207).  Elements are Fr Montgomery limbs (4 x u64 LE,
+ * R = 2^256) exactly as ark-ff stores them; natural order in and out; in place. */
+int32_t dg_fr_ntt(uint8_t *data, uint32_t logn, int32_t inverse, int32_t coset);
+/* device variant: data_dev and tmp_dev are 2^logn x 32 B device buffers (tmp is scratch) */
+int32_t dg_fr_ntt_device(void *data_dev, void *tmp_dev, uint32_t logn, int32_t inverse, int32_t coset, void *stream);
+/* Tail of LibsnarkReduction::witness_map_from_matrices (r1cs_to_qap.rs:187-207): a, b, c are the
+ * 2^logn constraint evaluations; out_h = coset_ifft((coset_fft(ifft a) * coset_fft(ifft b) -
+ * coset_fft(ifft c)) / Z(7)), the coefficients the h_query MSM consumes. */
+int32_t dg_qap_h_from_abc(const uint8_t *a, const uint8_t *b, const uint8_t *c, uint32_t logn, uint8_t *out_h);
+
 /* ---- measurement hooks (bench.py) ---------------------------------------------------------------
  * While enabled, every MSM records a CUDA-event pair on its launching stream around the bucket
  * accumulation kernel (the dominant kernel); dg_prof_read_accumulate synchronises the device,
@@ -153,6 +166,7 @@ int32_t dg_prof_read_accumulate(double *mean_ms, int32_t *count);
 
 /* ---- test hooks (field arithmetic parity; not part of the reference-facing surface) ---------- */
 int32_t dg_dbg_fp_op(int32_t op, const uint8_t *a, const uint8_t *b, size_t n, uint8_t *out);
+int32_t dg_dbg_fr_op(int32_t op, const uint8_t *a, const uint8_t *b, size_t n, uint8_t *out);
 
 #ifdef __cplusplus
 }

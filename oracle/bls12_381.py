@@ -637,3 +637,35 @@ class SplitMix64:
             v &= (1 << 255) - 1
             if v < R:
                 return v
+
+
+# ------------------------------------------------- Fr / NTT ------------
+FR_GENERATOR = 7
+FR_TWO_ADICITY = 32
+FR_TWO_ADIC_ROOT = pow(FR_GENERATOR, (R - 1) >> FR_TWO_ADICITY, R)
+# the constant ark-bls12-381 0.4 ships as FrConfig::TWO_ADIC_ROOT_OF_UNITY
+assert FR_TWO_ADIC_ROOT == 10238227357739495823651030575849232062558860180284477541189508159991286009131
+
+def fr_to_mont_bytes(a):
+    return ((a * FR_R) % R).to_bytes(32, 'little')
+
+def fr_from_mont_bytes(b):
+    return (int.from_bytes(b, 'little') * pow(FR_R, R - 2, R)) % R
+
+def fr_domain_generator(logn):
+    return pow(FR_TWO_ADIC_ROOT, 1 << (FR_TWO_ADICITY - logn), R)
+
+def fr_fft_definition(coeffs, logn, coset=False):
+    """evals[i] = sum_j a_j (off * g^i)^j : ark_poly Radix2EvaluationDomain::fft (coset: offset 7)."""
+    n = 1 << logn
+    g = fr_domain_generator(logn)
+    off = FR_GENERATOR if coset else 1
+    out = []
+    for i in range(n):
+        x = off * pow(g, i, R) % R
+        acc, xp = 0, 1
+        for a in coeffs:
+            acc = (acc + a * xp) % R
+            xp = xp * x % R
+        out.append(acc)
+    return out

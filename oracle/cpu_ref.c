@@ -525,3 +525,117 @@ EXPORT void ref_fp_mul(const uint8_t *a, const uint8_t *b, uint8_t *out) {
     fp_t x, y, r; memcpy(&x, a, 48); memcpy(&y, b, 48); fp_mul(&r, &x, &y); memcpy(out, &r, 48);
 }
 EXPORT void ref_fp_inv(const uint8_t *a, uint8_t *out) { fp_t x, r; memcpy(&x, a, 48); fp_inv(&r, &x); memcpy(out, &r, 48); }
+
+/* ================================================================= Fr / NTT ==================
+ * "Next" row f1 of SURVEY.md 8f: ark_poly::Radix2EvaluationDomain<Fr>::{fft,ifft}_in_place and
+ * the coset variants with offset Fr::GENERATOR = 7, as legogroth16's witness map uses them
+ * (legogroth16/src/r1cs_to_qap.rs:187-207).  ark-poly ^0.4.1 is not vendored; this restates the
+ * definition: group generator g = 7^((r-1)/n), evals[i] = sum_j a_j (off * g^i)^j, natural order
+ * in and out.  Elements are Montgomery limbs (4 x u64, R = 2^256) as ark-ff stores Fr. */
+typedef struct { uint64_t l[4]; } fr_t;
+static inline int fr_geq_mod(const uint64_t a[4]) {
+    for (int i = 3; i >= 0; i--) { if (a[i] > FRC_MOD[i]) return 1; if (a[i] < FRC_MOD[i]) return 0; }
+    return 1;
+}
+static inline void fr_sub_mod(uint64_t a[4]) {
+    u128 br = 0;
+    for (int i = 0; i < 4; i++) { u128 t = (u128)a[i] - FRC_MOD[i] - br; a[i] = (uint64_t)t; br = (t >> 64) & 1; }
+}
+static inline void fr_add(fr_t *r, const fr_t *a, const fr_t *b) {
+    u128 c = 0; uint64_t t[4];
+    for (int i = 0; i < 4; i++) { c += (u128)a->l[i] + b->l[i]; t[i] = (uint64_t)c; c >>= 64; }
+    if (c || fr_geq_mod(t)) fr_sub_mod(t);
+    memcpy(r->l, t, 32);
+}
+static inline void fr_sub(fr_t *r, const fr_t *a, const fr_t *b) {
+    u128 br = 0; uint64_t t[4];
+    for (int i = 0; i < 4; i++) { u128 d = (u128)a->l[i] - b->l[i] - br; t[i] = (uint64_t)d; br = (d >> 64) & 1; }
+    if (br) { u128 c = 0; for (int i = 0; i < 4; i++) { c += (u128)t[i] + FRC_MOD[i]; t[i] = (uint64_t)c; c >>= 64; } }
+    memcpy(r->l, t, 32);
+}
+static inline void fr_mul(fr_t *r, const fr_t *a, const fr_t *b) {
+    uint64_t t[6] = {0};
+    for (int i = 0; i < 4; i++) {
+        u128 c = 0;
+        for (int j = 0; j < 4; j++) { c += (u128)a->l[j] * b->l[i] + t[j]; t[j] = (uint64_t)c; c >>= 64; }
+        c += t[4]; t[4] = (uint64_t)c; t[5] = (uint64_t)(c >> 64);
+        uint64_t m = t[0] * FR_INV64;
+        c = (u128)m * FRC_MOD[0] + t[0]; c >>= 64;
+        for (int j = 1; j < 4; j++) { c += (u128)m * FRC_MOD[j] + t[j]; t[j - 1] = (uint64_t)c; c >>= 64; }
+        c += t[4]; t[3] = (uint64_t)c; t[4] = t[5] + (uint64_t)(c >> 64);
+    }
+    if (t[4] || fr_geq_mod(t)) fr_sub_mod(t);
+    memcpy(r->l, t, 32);
+}
+static void fr_pow_u64(fr_t *r, const fr_t *a, uint64_t e) {
+    fr_t acc; memcpy(acc.l, FRC_ONE, 32);
+    for (int i = 63; i >= 0; i--) { fr_mul(&acc, &acc, &acc); if ((e >> i) & 1) fr_mul(&acc, &acc, a); }
+    *r = acc;
+}
+static void fr_inv(fr_t *r, const fr_t *a) {                 /* a^(r-2) */
+    uint64_t e[4]; memcpy(e, FRC_MOD, 32); e[0] -= 2;
+    fr_t acc; memcpy(acc.l, FRC_ONE, 32);
+    for (int i = 255; i >= 0; i--) { fr_mul(&acc, &acc, &acc); if ((e[i >> 6] >> (i & 63)) & 1) fr_mul(&acc, &acc, a); }
+    *r = acc;
+}
+/* group generator of the size-2^logn domain: W32^(2^(32-logn)) */
+static void fr_domain_gen(fr_t *g, uint32_t logn) {
+    memcpy(g->l, FRC_W32, 32);
+    for (uint32_t i = logn; i < 32; i++) fr_mul(g, g, g);
+}
+/* in-place radix-2 DIT NTT, natural order in and out, `root` a primitive 2^logn-th root */
+static void fr_ntt_core(fr_t *a, uint32_t logn, const fr_t *root) {
+    size_t n = (size_t)1 << logn;
+    for (size_t i = 0; i < n; i++) {
+        size_t j = 0;
+        for (uint32_t b = 0; b < logn; b++) j |= ((i >> b) & 1) << (logn - 1 - b);
+        if (j > i) { fr_t t = a[i]; a[i] = a[j]; a[j] = t; }
+    }
+    fr_t *tw = (fr_t *)malloc(sizeof(fr_t) * (n / 2 ? n / 2 : 1));
+    memcpy(tw[0].l, FRC_ONE, 32);
+    for (size_t i = 1; i < n / 2; i++) fr_mul(&tw[i], &tw[i - 1], root);
+    for (uint32_t s = 1; s <= logn; s++) {
+        size_t m = (size_t)1 << (s - 1), step = n >> s;
+#pragma omp parallel for schedule(static)
+        for (size_t k = 0; k < n / 2; k++) {
+            size_t blk = k / m, j = k % m, lo = blk * 2 * m + j, hi = lo + m;
+            fr_t v; fr_mul(&v, &a[hi], &tw[j * step]);
+            fr_t u = a[lo];
+            fr_add(&a[lo], &u, &v); fr_sub(&a[hi], &u, &v);
+        }
+    }
+    free(tw);
+}
+EXPORT void ref_fr_ntt(uint8_t *data, uint32_t logn, int inverse, int coset) {
+    size_t n = (size_t)1 << logn;
+    fr_t *a = (fr_t *)data;
+    fr_t g, gen; fr_domain_gen(&g, logn); memcpy(gen.l, FRC_GEN, 32);
+    if (!inverse) {
+        if (coset) { fr_t p; memcpy(p.l, FRC_ONE, 32); for (size_t i = 0; i < n; i++) { fr_mul(&a[i], &a[i], &p); fr_mul(&p, &p, &gen); } }
+        fr_ntt_core(a, logn, &g);
+    } else {
+        fr_t gi; fr_inv(&gi, &g);
+        fr_ntt_core(a, logn, &gi);
+        fr_t nn, ninv, r2; memset(&nn, 0, sizeof nn); nn.l[0] = n; memcpy(r2.l, FRC_R2, 32);
+        fr_mul(&nn, &nn, &r2);                                   /* n in Montgomery form */
+        fr_inv(&ninv, &nn);
+        fr_t geninv; fr_inv(&geninv, &gen);
+        fr_t p = ninv;
+        for (size_t i = 0; i < n; i++) { fr_mul(&a[i], &a[i], &p); if (coset) fr_mul(&p, &p, &geninv); }
+    }
+}
+/* tail of LibsnarkReduction::witness_map_from_matrices (legogroth16/src/r1cs_to_qap.rs:187-207) */
+EXPORT void ref_qap_h_from_abc(const uint8_t *a_in, const uint8_t *b_in, const uint8_t *c_in, uint32_t logn, uint8_t *out_h) {
+    size_t n = (size_t)1 << logn;
+    fr_t *a = (fr_t *)malloc(32 * n), *b = (fr_t *)malloc(32 * n), *c = (fr_t *)malloc(32 * n);
+    memcpy(a, a_in, 32 * n); memcpy(b, b_in, 32 * n); memcpy(c, c_in, 32 * n);
+    fr_t *arr[3] = {a, b, c};
+    for (int k = 0; k < 3; k++) { ref_fr_ntt((uint8_t *)arr[k], logn, 1, 0); ref_fr_ntt((uint8_t *)arr[k], logn, 0, 1); }
+    fr_t gen, z, one, zinv; memcpy(gen.l, FRC_GEN, 32); memcpy(one.l, FRC_ONE, 32);
+    fr_pow_u64(&z, &gen, (uint64_t)n); fr_sub(&z, &z, &one); fr_inv(&zinv, &z);    /* 1 / (7^n - 1) */
+    for (size_t i = 0; i < n; i++) { fr_t t; fr_mul(&t, &a[i], &b[i]); fr_sub(&t, &t, &c[i]); fr_mul(&a[i], &t, &zinv); }
+    ref_fr_ntt((uint8_t *)a, logn, 1, 1);
+    memcpy(out_h, a, 32 * n);
+    free(a); free(b); free(c);
+}
+EXPORT void ref_fr_mul(const uint8_t *a, const uint8_t *b, uint8_t *out) { fr_t x, y, r; memcpy(&x, a, 32); memcpy(&y, b, 32); fr_mul(&r, &x, &y); memcpy(out, &r, 32); }

@@ -184,3 +184,17 @@ def random_scalars(n, seed):
         out[need[lt]] = v[lt]
         need = need[~lt]
     return out.view(np.uint8).reshape(-1)
+
+
+def fr_ntt(data, logn, inverse=False, coset=False):
+    """ark_poly Radix2EvaluationDomain fft / ifft (+ coset, offset 7) on Montgomery Fr records."""
+    a = np.array(_as_np(data), dtype=np.uint8, copy=True)
+    lib().ref_fr_ntt(a.ctypes.data_as(C.c_void_p), C.c_uint32(logn), C.c_int(1 if inverse else 0), C.c_int(1 if coset else 0))
+    return a
+
+
+def qap_h_from_abc(a, b, c, logn):
+    x, xp = _u8(_as_np(a)); y, yp = _u8(_as_np(b)); z, zp = _u8(_as_np(c))
+    out = np.zeros(32 << logn, np.uint8)
+    lib().ref_qap_h_from_abc(xp, yp, zp, C.c_uint32(logn), out.ctypes.data_as(C.c_void_p))
+    return out

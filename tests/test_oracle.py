@@ -139,3 +139,39 @@ def test_c_oracle_miller_matches_python(cref):
     p, q = bytes.fromhex(g['p']), bytes.fromhex(g['q'])
     ml = o.multi_miller_loop([o.g1_from_bytes(p)], [o.g2_from_bytes(q)])
     assert bytes(cref.multi_miller_loop(p, q)) == o.fp12_to_bytes(ml)
+
+
+# ------------------------------------------------------------------ Fr NTT (row f1) -----------
+def test_fr_root_of_unity_is_arkworks_constant():
+    assert o.FR_TWO_ADIC_ROOT == 10238227357739495823651030575849232062558860180284477541189508159991286009131
+    g = o.fr_domain_generator(19)
+    assert pow(g, 1 << 19, o.R) == 1 and pow(g, 1 << 18, o.R) != 1
+
+
+@pytest.mark.parametrize('logn', [0, 1, 3, 6])
+def test_c_oracle_ntt_vs_definition(cref, logn):
+    n = 1 << logn
+    rng = o.SplitMix64(logn + 1)
+    co = [rng.scalar() for _ in range(n)]
+    data = b''.join(o.fr_to_mont_bytes(c) for c in co)
+    for coset in (False, True):
+        ev = cref.fr_ntt(data, logn, False, coset)
+        assert bytes(ev) == b''.join(o.fr_to_mont_bytes(v) for v in o.fr_fft_definition(co, logn, coset))
+        assert bytes(cref.fr_ntt(ev, logn, True, coset)) == data
+
+
+def test_c_oracle_ntt_convolution(cref):
+    """ifft(fft(a) * fft(b)) is the cyclic convolution: pins the transform through polynomial products."""
+    logn, n = 5, 32
+    rng = o.SplitMix64(9)
+    a = [rng.scalar() for _ in range(n // 2)] + [0] * (n // 2)
+    b = [rng.scalar() for _ in range(n // 2)] + [0] * (n // 2)
+    enc = lambda v: b''.join(o.fr_to_mont_bytes(x) for x in v)
+    fa = [o.fr_from_mont_bytes(bytes(cref.fr_ntt(enc(a), logn)[32 * i:32 * i + 32])) for i in range(n)]
+    fb = [o.fr_from_mont_bytes(bytes(cref.fr_ntt(enc(b), logn)[32 * i:32 * i + 32])) for i in range(n)]
+    prod = cref.fr_ntt(enc([x * y % o.R for x, y in zip(fa, fb)]), logn, True)
+    exp = [0] * n
+    for i, x in enumerate(a):
+        for j, y in enumerate(b):
+            exp[(i + j) % n] = (exp[(i + j) % n] + x * y) % o.R
+    assert bytes(prod) == enc(exp)
