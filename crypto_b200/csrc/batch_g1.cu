@@ -27,6 +27,7 @@ int32_t bases_precompute_g1(HandleRec &rec, int c, cudaStream_t s) { return base
 extern "C" {
 int32_t dg_fixed_base_table_g1(const uint8_t *p, size_t hint_n, uint64_t *h) { return fixed_table_build<Fp>(p, hint_n, h); }
 int32_t dg_fixed_base_mul_many_g1(uint64_t h, const uint8_t *s, size_t m, uint8_t *o) { return fixed_mul_many<Fp>(h, s, m, o); }
+int32_t dg_fixed_base_mul_many_normalized_g1(uint64_t h, const uint8_t *s, size_t m, uint8_t *o) { return fixed_mul_many_normalized<Fp>(h, s, m, o); }
 int32_t dg_batch_mul_g1(const uint8_t *p, const uint8_t *s, size_t m, uint8_t *o) { return batch_mul<Fp>(p, s, m, o); }
 int32_t dg_batch_mul_add_fixed_g1(const uint8_t *p, const uint8_t *sa, uint64_t h, const uint8_t *sb, size_t m, uint8_t *o) {
     return batch_mul_add_fixed<Fp>(p, sa, h, sb, m, o);

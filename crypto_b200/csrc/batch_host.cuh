@@ -82,6 +82,33 @@ template <class F> static int32_t fixed_mul_many(uint64_t handle, const uint8_t 
     return DG_OK;
 }
 
+// FixedBase::msm followed by CurveGroup::normalize_batch without leaving the device
+// (legogroth16/src/generator.rs:335-425, vb_accumulator/src/batch_utils.rs:498-509): m affine records.
+template <class F> static int32_t fixed_mul_many_normalized(uint64_t handle, const uint8_t *scalars, size_t m, uint8_t *out_affine) {
+    int32_t rc = check_init();
+    if (rc) return rc;
+    if (m && (!scalars || !out_affine)) return fail(DG_ERR_BAD_ARG, "fixed_base_mul_many_normalized: null pointer");
+    HandleRec tb;
+    rc = lookup_table<F>(handle, tb);
+    if (rc) return rc;
+    if (m == 0) return DG_OK;
+    ThreadState &t = tls();
+    rc = t.arena.ensure(Arena::pad(32 * m) + Arena::pad(Sizes<F>::JAC * m) + Arena::pad(Sizes<F>::AFF * m) + Arena::pad(sizeof(F) * m),
+                        t.stream);
+    if (rc) return rc;
+    uint8_t *d_s = t.arena.alloc<uint8_t>(32 * m);
+    Jac<F> *d_j = t.arena.alloc<Jac<F>>(m);
+    Affine<F> *d_a = t.arena.alloc<Affine<F>>(m);
+    F *d_prefix = t.arena.alloc<F>(m);
+    DG_CUDA(cudaMemcpyAsync(d_s, scalars, 32 * m, cudaMemcpyHostToDevice, t.stream));
+    DG_LAUNCH(k_fixed_mul_many<F>, div_up(m, 128), 128, 0, t.stream, (const Affine<F> *)tb.dev, tb.window, tb.nwin, d_s,
+              (uint32_t)m, d_j);
+    normalize_device<F>(d_j, m, d_a, d_prefix, t.stream);
+    DG_CUDA(cudaMemcpyAsync(out_affine, d_a, Sizes<F>::AFF * m, cudaMemcpyDeviceToHost, t.stream));
+    DG_CUDA(cudaStreamSynchronize(t.stream));
+    return DG_OK;
+}
+
 template <class F> static int32_t batch_mul(const uint8_t *points, const uint8_t *scalars, size_t m, uint8_t *out_jac) {
     int32_t rc = check_init();
     if (rc) return rc;

@@ -22,6 +22,7 @@ EXPORTS = [
     'dg_fixed_base_table_g1', 'dg_fixed_base_table_g2', 'dg_fixed_base_table_info',
     'dg_fixed_base_table_download', 'dg_fixed_base_table_free',
     'dg_fixed_base_mul_many_g1', 'dg_fixed_base_mul_many_g2',
+    'dg_fixed_base_mul_many_normalized_g1', 'dg_fixed_base_mul_many_normalized_g2',
     'dg_batch_mul_g1', 'dg_batch_mul_g2', 'dg_batch_mul_add_fixed_g1',
     'dg_normalize_batch_g1', 'dg_normalize_batch_g2',
     'dg_multi_miller_loop', 'dg_final_exponentiation', 'dg_multi_pairing', 'dg_multi_pairing_is_one',
@@ -195,6 +196,17 @@ class FixedBaseTable:
         rec = G2_JAC if self.g2 else G1_JAC
         o, op = _out(rec * m)
         fn = lib.dg_fixed_base_mul_many_g2 if self.g2 else lib.dg_fixed_base_mul_many_g1
+        _check(fn(C.c_uint64(self.handle), sp, C.c_size_t(m), op))
+        return o[:rec * m]
+
+    def mul_many_normalized(self, scalars):
+        """FixedBase::msm + normalize_batch fused on the device -> m affine records."""
+        lib = load()
+        s, sp = _in(scalars)
+        m = s.size // SCALAR
+        rec = G2_AFF if self.g2 else G1_AFF
+        o, op = _out(rec * m)
+        fn = lib.dg_fixed_base_mul_many_normalized_g2 if self.g2 else lib.dg_fixed_base_mul_many_normalized_g1
         _check(fn(C.c_uint64(self.handle), sp, C.c_size_t(m), op))
         return o[:rec * m]
 

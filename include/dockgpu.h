@@ -106,6 +106,10 @@ int32_t dg_fixed_base_table_free(uint64_t table_handle);
  * = FixedBase::msm: out m Jacobian points. */
 int32_t dg_fixed_base_mul_many_g1(uint64_t table_handle, const uint8_t *scalars, size_t m, uint8_t *out_jac);
 int32_t dg_fixed_base_mul_many_g2(uint64_t table_handle, const uint8_t *scalars, size_t m, uint8_t *out_jac);
+/* FixedBase::msm + CurveGroup::normalize_batch fused on the device: m affine records
+ * (legogroth16/src/generator.rs:335-425 CRS generation, "next" row f2; vb_accumulator/src/batch_utils.rs:498-509 Omega::new). */
+int32_t dg_fixed_base_mul_many_normalized_g1(uint64_t table_handle, const uint8_t *scalars, size_t m, uint8_t *out_affine);
+int32_t dg_fixed_base_mul_many_normalized_g2(uint64_t table_handle, const uint8_t *scalars, size_t m, uint8_t *out_affine);
 
 /* ---- independent scalar multiplications ----------------------------------------------------
  * AffineRepr::mul_bigint inside cfg_iter! maps (vb_accumulator/src/witness.rs:190,229,278;

@@ -19,3 +19,8 @@ def test_config4_bbs_plus_and_accumulator_shape(dg):
     res = rw.config4(500, with_cpu=False)
     assert res['sign_msm']['ok'] and res['verify_2pair_check']['ok']
     assert res['multi_pairing_256']['ok'] and res['witness_update']['ok']
+
+
+def test_next_f2_crs_generator_shape(dg):
+    res = rw.config_generator(9, with_cpu=False)
+    assert len(res['tables']) == 6 and all(t['ok'] for t in res['tables'])

@@ -144,6 +144,39 @@ def config4(nmsg, with_cpu):
     return res
 
 
+def config_generator(logd, with_cpu):
+    """'Next' row f2: legogroth16 CRS generation (legogroth16/src/generator.rs:335-425): FixedBase::msm of
+    one generator over D scalars, five times in G1 and once in G2, each followed by normalize_batch."""
+    n = 1 << logd
+    res = {'D': n, 'tables': []}
+    for name, g2, seed in (('a_query', False, 1), ('b_g1_query', False, 2), ('h_query', False, 3), ('l_query', False, 4),
+                           ('gamma_abc', False, 5), ('b_g2_query', True, 6)):
+        base = (cref.g2_generator_muls if g2 else cref.g1_generator_muls)(cref.random_scalars(1, 60 + seed))
+        ss = cref.random_scalars(n, 70 + seed).copy()
+        ss[:64] = 0                                   # scalar 0 -> identity points in the queries (generator.rs:342,373)
+        t = lib.FixedBaseTable(base, n, g2=g2)
+        dt, out = timeit(lambda: t.mul_many_normalized(ss), reps=2)
+        t.free()
+        k = 64                                        # check the first 64 against per-scalar mul_bigint on the oracle
+        exp = (cref.normalize_batch_g2(cref.batch_mul_g2(np.tile(base, k), ss[:32 * k])) if g2
+               else cref.normalize_batch_g1(cref.batch_mul_g1(np.tile(base, k), ss[:32 * k])))
+        rec = 192 if g2 else 96
+        ent = {'name': name, 'group': 'G2' if g2 else 'G1', 'scalars': n, 'gpu_ms': dt * 1e3, 'ok': bytes(out[:rec * k]) == bytes(exp)}
+        if with_cpu:
+            tt = time.perf_counter()
+            if g2:
+                j, _, _ = cref.fixed_base_mul_many_g2(base, n, ss); cref.normalize_batch_g2(j)
+            else:
+                j, _, _ = cref.fixed_base_mul_many_g1(base, n, ss); cref.normalize_batch_g1(j)
+            ent['cpu_ms'] = (time.perf_counter() - tt) * 1e3
+        res['tables'].append(ent)
+        print('  ', ent, flush=True)
+    res['gpu_ms_total'] = sum(e['gpu_ms'] for e in res['tables'])
+    if with_cpu:
+        res['cpu_ms_total'] = sum(e['cpu_ms'] for e in res['tables'])
+    return res
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--logd', type=int, default=18)
@@ -158,6 +191,8 @@ def main():
     out['config3_legogroth16_prover_shape'] = config3(a.logd, not a.no_cpu)
     print('config 4', flush=True)
     out['config4_bbs_plus_and_accumulator_shape'] = config4(a.messages, not a.no_cpu)
+    print('generator (row f2)', flush=True)
+    out['next_f2_crs_generator_shape'] = config_generator(a.logd, not a.no_cpu)
     s = json.dumps(out, indent=1)
     if a.out:
         open(a.out, 'w').write(s)
