@@ -70,7 +70,8 @@ static int32_t read_err_flag(ThreadState &t, const char *what) {
 }
 
 template <bool G2>
-static int32_t msm_host(uint64_t handle, const uint8_t *bases, const uint8_t *scalars, size_t n, uint8_t *out_jac) {
+static int32_t msm_host(uint64_t handle, const uint8_t *bases, const uint8_t *scalars, size_t n, uint8_t *out_jac,
+                        bool mont_scalars = false) {
     int32_t rc = check_init();
     if (rc) return rc;
     const size_t PT = G2 ? 192 : 96, JAC = G2 ? 288 : 144;
@@ -95,6 +96,7 @@ static int32_t msm_host(uint64_t handle, const uint8_t *bases, const uint8_t *sc
     uint8_t *d_scalars = t.arena.alloc<uint8_t>(32 * n);
     uint8_t *d_out = t.arena.alloc<uint8_t>(JAC);
     if (n) DG_CUDA(cudaMemcpyAsync(d_scalars, scalars, 32 * n, cudaMemcpyHostToDevice, t.stream));
+    if (n && mont_scalars) fr_into_bigint_device(d_scalars, d_scalars, n, t.stream);   // msm_unchecked: into_bigint first
     if (!handle && n) {
         uint8_t *d_bases = t.arena.alloc<uint8_t>(PT * n);
         DG_CUDA(cudaMemcpyAsync(d_bases, bases, PT * n, cudaMemcpyHostToDevice, t.stream));
@@ -225,6 +227,8 @@ int32_t dg_bases_free(uint64_t handle) {
 
 int32_t dg_msm_g1(uint64_t h, const uint8_t *bases, const uint8_t *scalars, size_t n, uint8_t *out) { return msm_host<false>(h, bases, scalars, n, out); }
 int32_t dg_msm_g2(uint64_t h, const uint8_t *bases, const uint8_t *scalars, size_t n, uint8_t *out) { return msm_host<true>(h, bases, scalars, n, out); }
+int32_t dg_msm_unchecked_g1(uint64_t h, const uint8_t *bases, const uint8_t *fr_mont, size_t n, uint8_t *out) { return msm_host<false>(h, bases, fr_mont, n, out, true); }
+int32_t dg_msm_unchecked_g2(uint64_t h, const uint8_t *bases, const uint8_t *fr_mont, size_t n, uint8_t *out) { return msm_host<true>(h, bases, fr_mont, n, out, true); }
 int32_t dg_msm_g1_device(const void *b, const void *s, size_t n, void *o, void *st) { return msm_device<false>(0, b, s, n, o, st); }
 int32_t dg_msm_g2_device(const void *b, const void *s, size_t n, void *o, void *st) { return msm_device<true>(0, b, s, n, o, st); }
 int32_t dg_msm_g1_handle_device(uint64_t h, const void *s, size_t n, void *o, void *st) {

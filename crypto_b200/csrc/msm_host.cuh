@@ -76,6 +76,8 @@ static int32_t msm_run(const void *bases_dev, const void *scalars_dev, size_t n,
         return DG_OK;
     }
     if (n >= (1ull << 31)) return fail(DG_ERR_BAD_ARG, "msm: n must be < 2^31");
+    if ((uint64_t)n * msm_geometry(n, pre).ndig >= 0xffffffffull)
+        return fail(DG_ERR_BAD_ARG, "msm: n * digits must fit 32-bit entry offsets (n up to ~2^27)");
     if (pre.c && (uint64_t)pre.row_stride * ((256 + pre.c - 1) / pre.c) >= (1ull << 31))
         return fail(DG_ERR_BAD_ARG, "msm: precomputed table too large for 31-bit point indices");
     MsmLayout m = msm_layout<F>(n, pre);

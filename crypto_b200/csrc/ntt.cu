@@ -153,6 +153,19 @@ __global__ void __launch_bounds__(128) k_dbg_fr_op(int op, const Fr *a, const Fr
     fr_store(&out[i], r);
 }
 
+// Fr::into_bigint(): Montgomery -> canonical integer = Montgomery product with the plain integer 1
+__global__ void __launch_bounds__(256) k_fr_into_bigint(const Fr *__restrict__ in, Fr *__restrict__ out, uint32_t n) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    Fr one = fr_zero();
+    one.l[0] = 1;
+    fr_store(&out[i], fr_mul(fr_load(&in[i]), one));
+}
+int32_t fr_into_bigint_device(const void *in, void *out, size_t n, cudaStream_t s) {
+    if (n) DG_LAUNCH(k_fr_into_bigint, div_up(n, 256), 256, 0, s, (const Fr *)in, (Fr *)out, (uint32_t)n);
+    return DG_OK;
+}
+
 static int32_t get_plan(uint32_t logn, cudaStream_t s, NttPlan &out) {
     std::lock_guard<std::mutex> lk(ctx().mu);
     auto it = plans().find(logn);
@@ -239,6 +252,22 @@ int32_t dg_fr_ntt_device(void *data_dev, void *tmp_dev, uint32_t logn, int32_t i
     if (!data_dev || !tmp_dev) return fail(DG_ERR_BAD_ARG, "fr_ntt_device: null pointer");
     cudaStream_t s = stream ? (cudaStream_t)stream : tls().stream;
     return ntt_device((Fr *)data_dev, (Fr *)tmp_dev, logn, inverse != 0, coset != 0, s);
+}
+
+int32_t dg_fr_into_bigint(const uint8_t *fr_mont, size_t n, uint8_t *out_canonical) {
+    int32_t rc = check_init();
+    if (rc) return rc;
+    if (n && (!fr_mont || !out_canonical)) return fail(DG_ERR_BAD_ARG, "fr_into_bigint: null pointer");
+    if (n == 0) return DG_OK;
+    ThreadState &t = tls();
+    rc = t.arena.ensure(Arena::pad(32 * n), t.stream);
+    if (rc) return rc;
+    Fr *d = t.arena.alloc<Fr>(n);
+    DG_CUDA(cudaMemcpyAsync(d, fr_mont, 32 * n, cudaMemcpyHostToDevice, t.stream));
+    fr_into_bigint_device(d, d, n, t.stream);
+    DG_CUDA(cudaMemcpyAsync(out_canonical, d, 32 * n, cudaMemcpyDeviceToHost, t.stream));
+    DG_CUDA(cudaStreamSynchronize(t.stream));
+    return DG_OK;
 }
 
 // test hook: out[i] = a[i] (op) b[i]  with op 0 mul, 1 add, 2 sub, 3 inverse(a)

@@ -562,11 +562,77 @@ static int32_t pairing_run(const uint8_t *g1, const uint8_t *g2, size_t k, int m
     return DG_OK;
 }
 
+// Several independent pairing products at once (SnarkPack's GIPA rounds issue six per round,
+// legogroth16/src/aggregation/utils.rs:85-97): one k_miller launch covers every pair of every
+// product, then each product's CTA tree + final exponentiation runs on its own stream so the
+// latency-bound tails overlap instead of queueing behind each other.
+#define DG_PAIR_STREAMS 8
+static int32_t pairing_batch_run(const uint8_t *g1, const uint8_t *g2, const size_t *counts, size_t nbatch, uint8_t *out_fp12) {
+    int32_t rc = check_init();
+    if (rc) return rc;
+    if (!counts || !out_fp12 || nbatch == 0) return fail(DG_ERR_BAD_ARG, "multi_pairing_batch: null pointer");
+    size_t k = 0;
+    for (size_t i = 0; i < nbatch; i++) k += counts[i];
+    if (k && (!g1 || !g2)) return fail(DG_ERR_BAD_ARG, "multi_pairing_batch: null pointer");
+    rc = pairing_smem_opt_in();
+    if (rc) return rc;
+    ThreadState &t = tls();
+    static thread_local cudaStream_t aux[DG_PAIR_STREAMS] = {nullptr};
+    static thread_local cudaEvent_t ev_fork = nullptr, ev_join[DG_PAIR_STREAMS] = {nullptr};
+    if (!ev_fork) {
+        DG_CUDA(cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming));
+        for (int i = 0; i < DG_PAIR_STREAMS; i++) {
+            DG_CUDA(cudaStreamCreateWithFlags(&aux[i], cudaStreamNonBlocking));
+            DG_CUDA(cudaEventCreateWithFlags(&ev_join[i], cudaEventDisableTiming));
+        }
+    }
+    size_t need = Arena::pad(96 * k) + Arena::pad(192 * k) + 2 * Arena::pad(sizeof(F12) * (k + nbatch)) + Arena::pad(sizeof(F12) * nbatch) + 256;
+    rc = t.arena.ensure(need, t.stream);
+    if (rc) return rc;
+    Affine<Fp> *d_p = t.arena.alloc<Affine<Fp>>(k ? k : 1);
+    Affine<Fp2> *d_q = t.arena.alloc<Affine<Fp2>>(k ? k : 1);
+    F12 *buf0 = t.arena.alloc<F12>(k + nbatch), *buf1 = t.arena.alloc<F12>(k + nbatch), *d_out = t.arena.alloc<F12>(nbatch);
+    if (k) {
+        DG_CUDA(cudaMemcpyAsync(d_p, g1, 96 * k, cudaMemcpyHostToDevice, t.stream));
+        DG_CUDA(cudaMemcpyAsync(d_q, g2, 192 * k, cudaMemcpyHostToDevice, t.stream));
+        DG_LAUNCH(k_miller, (unsigned)k, PAIR_THREADS, sizeof(PairSmem), t.stream, d_p, d_q, (uint32_t)k, buf0);
+    }
+    DG_CUDA(cudaEventRecord(ev_fork, t.stream));
+    size_t off = 0;
+    for (size_t b = 0; b < nbatch; b++) {
+        cudaStream_t s = aux[b % DG_PAIR_STREAMS];
+        DG_CUDA(cudaStreamWaitEvent(s, ev_fork, 0));
+        size_t n = counts[b];
+        F12 *src = buf0 + off, *dst = buf1 + off;
+        const F12 *cur = n ? src : nullptr;
+        while (n > 1) {
+            unsigned nb = div_up(n, 8);
+            DG_LAUNCH(k_f12_reduce8, nb, PAIR_THREADS, sizeof(PairSmem), s, src, (uint32_t)n, dst);
+            F12 *tmp = src; src = dst; dst = tmp;
+            n = nb;
+            cur = src;
+        }
+        DG_LAUNCH(k_f12_finish, 1, PAIR_THREADS, sizeof(PairSmem), s, cur, 3, d_out + b, (int32_t *)nullptr);
+        off += counts[b];
+    }
+    for (size_t b = 0; b < nbatch && b < DG_PAIR_STREAMS; b++) {
+        DG_CUDA(cudaEventRecord(ev_join[b], aux[b]));
+        DG_CUDA(cudaStreamWaitEvent(t.stream, ev_join[b], 0));
+    }
+    DG_CUDA(cudaMemcpyAsync(out_fp12, d_out, sizeof(F12) * nbatch, cudaMemcpyDeviceToHost, t.stream));
+    DG_CUDA(cudaStreamSynchronize(t.stream));
+    return DG_OK;
+}
+
 }  // namespace dg
 
 using namespace dg;
 
 extern "C" {
+
+int32_t dg_multi_pairing_batch(const uint8_t *g1, const uint8_t *g2, const size_t *counts, size_t nbatch, uint8_t *out_fp12) {
+    return pairing_batch_run(g1, g2, counts, nbatch, out_fp12);
+}
 
 int32_t dg_multi_miller_loop(const uint8_t *g1, const uint8_t *g2, size_t k, uint8_t *out_fp12) {
     if (!out_fp12) return fail(DG_ERR_BAD_ARG, "multi_miller_loop: null output");

@@ -18,6 +18,7 @@ EXPORTS = [
     'dg_init', 'dg_shutdown', 'dg_last_error', 'dg_launch_count', 'dg_sync',
     'dg_bases_upload_g1', 'dg_bases_upload_g2', 'dg_bases_free', 'dg_bases_precompute',
     'dg_msm_g1_handle_device', 'dg_msm_g2_handle_device',
+    'dg_msm_unchecked_g1', 'dg_msm_unchecked_g2', 'dg_fr_into_bigint',
     'dg_msm_g1', 'dg_msm_g2', 'dg_msm_g1_device', 'dg_msm_g2_device', 'dg_msm_set_window',
     'dg_fixed_base_table_g1', 'dg_fixed_base_table_g2', 'dg_fixed_base_table_info',
     'dg_fixed_base_table_download', 'dg_fixed_base_table_free',
@@ -25,7 +26,7 @@ EXPORTS = [
     'dg_fixed_base_mul_many_normalized_g1', 'dg_fixed_base_mul_many_normalized_g2',
     'dg_batch_mul_g1', 'dg_batch_mul_g2', 'dg_batch_mul_add_fixed_g1',
     'dg_normalize_batch_g1', 'dg_normalize_batch_g2',
-    'dg_multi_miller_loop', 'dg_final_exponentiation', 'dg_multi_pairing', 'dg_multi_pairing_is_one',
+    'dg_multi_miller_loop', 'dg_final_exponentiation', 'dg_multi_pairing', 'dg_multi_pairing_is_one', 'dg_multi_pairing_batch',
     'dg_gt_pow', 'dg_fp12_mul',
     'dg_fold_g1', 'dg_fold_g1_device', 'dg_fold_g2',
     'dg_fr_ntt', 'dg_fr_ntt_device', 'dg_qap_h_from_abc',
@@ -145,6 +146,32 @@ def msm(bases, scalars, g2=False, n=None):
         k = min(ns, b.size // (G2_AFF if g2 else G1_AFF)) if n is None else n
         _check(fn(C.c_uint64(0), bp if k else None, sp, C.c_size_t(k), op))
     return o[:G2_JAC if g2 else G1_JAC]
+
+
+def msm_unchecked(bases, scalars_fr_mont, g2=False):
+    """msm_unchecked semantics: scalars are Fr Montgomery records, converted on the device."""
+    lib = init()
+    s, sp = _in(scalars_fr_mont)
+    ns = s.size // SCALAR
+    fn = lib.dg_msm_unchecked_g2 if g2 else lib.dg_msm_unchecked_g1
+    o, op = _out(G2_JAC if g2 else G1_JAC)
+    if isinstance(bases, Bases):
+        k = min(ns, bases.n)
+        _check(fn(C.c_uint64(bases.handle), None, sp, C.c_size_t(k), op))
+    else:
+        b, bp = _in(bases)
+        k = min(ns, b.size // (G2_AFF if g2 else G1_AFF))
+        _check(fn(C.c_uint64(0), bp if k else None, sp, C.c_size_t(k), op))
+    return o[:G2_JAC if g2 else G1_JAC]
+
+
+def fr_into_bigint(fr_mont):
+    lib = init()
+    s, sp = _in(fr_mont)
+    n = s.size // SCALAR
+    o, op = _out(32 * n)
+    _check(lib.dg_fr_into_bigint(sp, C.c_size_t(n), op))
+    return o[:32 * n]
 
 
 def msm_device(bases_ptr, scalars_ptr, n, out_ptr, stream=0, g2=False):
@@ -288,6 +315,17 @@ def multi_pairing(g1s, g2s):
     o, op = _out(FP12)
     _check(lib.dg_multi_pairing(ap, bp, C.c_size_t(k), op))
     return o[:FP12]
+
+
+def multi_pairing_batch(g1s, g2s, counts):
+    """Independent pairing products in one call -> list of 576-byte GT records."""
+    lib = init()
+    a, ap = _in(g1s); b, bp = _in(g2s)
+    nb = len(counts)
+    cnt = (C.c_size_t * nb)(*counts)
+    o, op = _out(FP12 * nb)
+    _check(lib.dg_multi_pairing_batch(ap, bp, cnt, C.c_size_t(nb), op))
+    return [o[FP12 * i:FP12 * (i + 1)] for i in range(nb)]
 
 
 def multi_pairing_is_one(g1s, g2s):

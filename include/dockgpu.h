@@ -82,6 +82,13 @@ int32_t dg_bases_precompute(uint64_t handle, int32_t window_bits);
  * smaller than the uploaded count (prefix).  out: one Jacobian point. */
 int32_t dg_msm_g1(uint64_t bases_handle, const uint8_t *bases, const uint8_t *scalars, size_t n, uint8_t *out_jac);
 int32_t dg_msm_g2(uint64_t bases_handle, const uint8_t *bases, const uint8_t *scalars, size_t n, uint8_t *out_jac);
+/* ark_ec::VariableBaseMSM::msm_unchecked(bases, &[Fr]): scalars arrive as Fr Montgomery limbs (R = 2^256,
+ * the in-memory form of ark-ff) and are mapped to canonical integers on the device (into_bigint) before
+ * the MSM -- the form bbs_plus/src/setup.rs:145 and schnorr_pok/src/pok_generalized_pedersen.rs:97 call. */
+int32_t dg_msm_unchecked_g1(uint64_t bases_handle, const uint8_t *bases, const uint8_t *scalars_fr_mont, size_t n, uint8_t *out_jac);
+int32_t dg_msm_unchecked_g2(uint64_t bases_handle, const uint8_t *bases, const uint8_t *scalars_fr_mont, size_t n, uint8_t *out_jac);
+/* Fr::into_bigint for n elements (Montgomery -> canonical little-endian integers) */
+int32_t dg_fr_into_bigint(const uint8_t *fr_mont, size_t n, uint8_t *out_canonical);
 /* device-pointer variants; out_jac_dev is device memory (144 / 288 B) */
 int32_t dg_msm_g1_device(const void *bases_dev, const void *scalars_dev, size_t n, void *out_jac_dev, void *stream);
 int32_t dg_msm_g2_device(const void *bases_dev, const void *scalars_dev, size_t n, void *out_jac_dev, void *stream);
@@ -134,6 +141,12 @@ int32_t dg_normalize_batch_g2(const uint8_t *jac, size_t m, uint8_t *out_affine)
 int32_t dg_multi_miller_loop(const uint8_t *g1_affine, const uint8_t *g2_affine, size_t k, uint8_t *out_fp12);
 int32_t dg_final_exponentiation(const uint8_t *in_fp12, uint8_t *out_fp12, int32_t *is_some);
 int32_t dg_multi_pairing(const uint8_t *g1_affine, const uint8_t *g2_affine, size_t k, uint8_t *out_fp12);
+/* nbatch independent pairing products in one call: product b covers counts[b] consecutive pairs of the
+ * concatenated inputs; out_fp12 receives nbatch x 576 B.  The Miller loops share one launch and the
+ * per-product tails (CTA product tree + final exponentiation) overlap on separate streams -- SnarkPack's
+ * GIPA rounds issue six multi_pairings per round (legogroth16/src/aggregation/utils.rs:85-97). */
+int32_t dg_multi_pairing_batch(const uint8_t *g1_affine, const uint8_t *g2_affine, const size_t *counts, size_t nbatch,
+                               uint8_t *out_fp12);
 /* result = 1 iff prod e(P_i, Q_i) == 1 */
 int32_t dg_multi_pairing_is_one(const uint8_t *g1_affine, const uint8_t *g2_affine, size_t k, int32_t *result);
 /* Target-group helpers used by RandomizedPairingChecker (right += out * m, left *= miller):

@@ -324,3 +324,28 @@ def test_msm_precomputed_g2_and_default_window(dg, cref):
         assert h.affine_g2(dg.msm(hb, ss, g2=True)) == h.known_dlog_msm_g2(ks, ss)
     finally:
         hb.free()
+
+
+def test_msm_unchecked_montgomery_scalars(dg, cref):
+    """msm_unchecked: Fr scalars in ark-ff's Montgomery form are converted on the device (into_bigint)."""
+    n = 777
+    bases, ks = h.g1_bases(n, 601)
+    ss = h.rand_scalars(n, 602)
+    mont = b''.join(o.fr_to_mont_bytes(v) for v in h.ints_of(ss))
+    assert bytes(dg.fr_into_bigint(mont)) == bytes(ss)
+    assert h.affine_g1(dg.msm_unchecked(bases, mont)) == h.known_dlog_msm_g1(ks, ss)
+    b2, k2 = h.g2_bases(50, 603)
+    assert h.affine_g2(dg.msm_unchecked(b2, mont[:32 * 50], g2=True)) == h.known_dlog_msm_g2(k2, ss[:32 * 50])
+
+
+def test_multi_pairing_batch(dg, cref):
+    ps, _ = h.g1_bases(30, 130)
+    qs, _ = h.g2_bases(30, 131)
+    ps = ps.copy(); ps[96 * 3:96 * 4] = 0
+    counts = [1, 9, 0, 12, 8]
+    outs = dg.multi_pairing_batch(ps, qs, counts)
+    off = 0
+    for c, got in zip(counts, outs):
+        exp = cref.multi_pairing(ps[96 * off:96 * (off + c)], qs[192 * off:192 * (off + c)]) if c else cref.fp12_one()
+        assert bytes(got) == bytes(exp)
+        off += c

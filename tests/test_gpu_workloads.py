@@ -24,3 +24,9 @@ def test_config4_bbs_plus_and_accumulator_shape(dg):
 def test_next_f2_crs_generator_shape(dg):
     res = rw.config_generator(9, with_cpu=False)
     assert len(res['tables']) == 6 and all(t['ok'] for t in res['tables'])
+
+
+def test_next_f3_snarkpack_shape(dg):
+    res = rw.config_snarkpack(16, with_cpu=True)
+    assert all(r['ok'] for r in res['rounds']) and res['z_c_msm']['ok']
+    assert res['pairs_total'] == 10 * 15

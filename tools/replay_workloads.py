@@ -177,6 +177,46 @@ def config_generator(logd, with_cpu):
     return res
 
 
+def config_snarkpack(nproofs, with_cpu):
+    """'Next' row f3: SnarkPack TIPP/MIPP prover shape (legogroth16/src/aggregation/utils.rs:85-97,
+    commitment.rs:40-66, groth16/prover.rs:114-116): per GIPA round with half-size m, four multi_pairings of
+    2m pairs (two PairCommitment::double) and two of m pairs, then one MSM of n terms."""
+    n = nproofs
+    a = cref.g1_generator_muls(cref.random_scalars(2 * n, 81))
+    b = cref.g2_generator_muls(cref.random_scalars(2 * n, 82))
+    res = {'proofs': n, 'rounds': []}
+    gpu_total = cpu_total = 0.0
+    pairs_total = 0
+    m = n // 2
+    while m >= 1:
+        sizes = [2 * m, 2 * m, 2 * m, 2 * m, m, m]
+        t = time.perf_counter()
+        outs = lib.multi_pairing_batch(np.concatenate([a[:96 * k] for k in sizes]), np.concatenate([b[:192 * k] for k in sizes]), sizes)
+        g = time.perf_counter() - t
+        ent = {'m': m, 'pairs': sum(sizes), 'gpu_ms': g * 1e3}
+        gpu_total += g
+        pairs_total += sum(sizes)
+        if with_cpu:
+            t = time.perf_counter()
+            exp = [cref.multi_pairing(a[:96 * k], b[:192 * k]) for k in sizes]
+            c = time.perf_counter() - t
+            ent['cpu_ms'] = c * 1e3
+            cpu_total += c
+            ent['ok'] = all(bytes(x) == bytes(y) for x, y in zip(outs, exp))
+        res['rounds'].append(ent)
+        m //= 2
+    ks = cref.random_scalars(n, 83); ss = cref.random_scalars(n, 84)
+    cpts = cref.g1_generator_muls(ks)
+    dt, out = timeit(lambda: lib.msm(cpts, ss))
+    res['z_c_msm'] = {'terms': n, 'gpu_ms': dt * 1e3,
+                      'ok': bytes(cref.normalize_batch_g1(out)) == bytes(cref.g1_generator_muls(sbytes([dlog_total(ks, ss)])))}
+    res['pairs_total'] = pairs_total
+    res['gpu_ms_total_pairings'] = gpu_total * 1e3
+    if with_cpu:
+        res['cpu_ms_total_pairings'] = cpu_total * 1e3
+    return res
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--logd', type=int, default=18)
@@ -193,6 +233,8 @@ def main():
     out['config4_bbs_plus_and_accumulator_shape'] = config4(a.messages, not a.no_cpu)
     print('generator (row f2)', flush=True)
     out['next_f2_crs_generator_shape'] = config_generator(a.logd, not a.no_cpu)
+    print('snarkpack (row f3)', flush=True)
+    out['next_f3_snarkpack_prover_shape'] = config_snarkpack(256, not a.no_cpu)
     s = json.dumps(out, indent=1)
     if a.out:
         open(a.out, 'w').write(s)
