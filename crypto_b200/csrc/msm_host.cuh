@@ -105,8 +105,15 @@ static int32_t msm_run(const void *bases_dev, const void *scalars_dev, size_t n,
         DG_CUDA(cudaEventCreate(&pe1));
         DG_CUDA(cudaEventRecord(pe0, s));
     }
-    DG_LAUNCH(k_accumulate<F>, div_up(m.nchunks, 128), 128, 0, s, (const Affine<F> *)bases_dev, entries, off, g.nb, m.L,
-              buckets, head, tail);
+    {
+        static bool smem_opt_in = false;                   // the Fp2 staging buffers exceed the 48 KB default
+        if (!smem_opt_in) {
+            DG_CUDA(cudaFuncSetAttribute(k_accumulate<F>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dg_acc_smem_bytes<F>()));
+            smem_opt_in = true;
+        }
+    }
+    DG_LAUNCH(k_accumulate<F>, div_up(m.nchunks, DG_ACC_THREADS), DG_ACC_THREADS, dg_acc_smem_bytes<F>(), s,
+              (const Affine<F> *)bases_dev, entries, off, g.nb, m.L, buckets, head, tail);
     if (pe0) {
         DG_CUDA(cudaEventRecord(pe1, s));
         std::lock_guard<std::mutex> lk(ctx().mu);

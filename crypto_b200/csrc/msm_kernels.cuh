@@ -142,17 +142,59 @@ static __global__ void __launch_bounds__(1024) k_scan_add(uint32_t *__restrict__
 // Thread t owns entries [t*L, (t+1)*L).  Runs (maximal same-bucket stretches inside the chunk):
 //   first run of the chunk  -> head[t]       last run (if not also first) -> tail[t]
 //   runs strictly inside    -> buckets[b] directly (nobody else touches that bucket)
+// ---- per-thread TMA staging of the gathered points ---------------------------------------------
+// The base of the NEXT entry is fetched by a bulk asynchronous copy (cp.async.bulk, the TMA engine;
+// UBLKCP in SASS) into a per-thread double buffer in shared memory while the current mixed addition
+// runs, completion tracked by a per-thread mbarrier (transaction bytes).  The gather latency
+// (L2 / HBM, the table of precomputed multiples does not fit L2) leaves the critical path and no
+// registers are spent on the prefetched point.
+__device__ __forceinline__ uint32_t dg_smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void dg_mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(dg_smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void dg_bulk_fetch(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
+    // order this thread's earlier generic-proxy reads of `dst` before the async-proxy write
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(dg_smem_u32(bar)), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dg_smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(dg_smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void dg_mbar_wait(uint64_t *bar, uint32_t parity) {
+    uint32_t done;
+    do {
+        asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}"
+                     : "=r"(done)
+                     : "r"(dg_smem_u32(bar)), "r"(parity)
+                     : "memory");
+    } while (!done);
+}
+#define DG_ACC_THREADS 128
+template <class F> constexpr size_t dg_acc_smem_bytes() { return (2 * sizeof(Affine<F>) + 16) * DG_ACC_THREADS; }
+
 template <class F>
-__global__ void __launch_bounds__(128, (sizeof(F) > 48 ? 2 : 3)) k_accumulate(const Affine<F> *__restrict__ bases, const uint32_t *__restrict__ entries,
+__global__ void __launch_bounds__(DG_ACC_THREADS, (sizeof(F) > 48 ? 2 : 3)) k_accumulate(const Affine<F> *__restrict__ bases, const uint32_t *__restrict__ entries,
                                                        const uint32_t *__restrict__ off, uint32_t nb, uint32_t L,
                                                        XYZZ<F> *__restrict__ buckets, XYZZ<F> *__restrict__ head,
                                                        XYZZ<F> *__restrict__ tail) {
+    extern __shared__ __align__(16) unsigned char dg_acc_smem[];
+    constexpr uint32_t REC = sizeof(Affine<F>);
+    unsigned char *stage[2] = {dg_acc_smem + (size_t)threadIdx.x * REC, dg_acc_smem + (size_t)(DG_ACC_THREADS + threadIdx.x) * REC};
+    uint64_t *bars = reinterpret_cast<uint64_t *>(dg_acc_smem + 2 * (size_t)DG_ACC_THREADS * REC);
+    uint64_t *bar[2] = {&bars[threadIdx.x], &bars[DG_ACC_THREADS + threadIdx.x]};
+
     uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
     uint32_t M = off[nb];
     uint64_t start64 = (uint64_t)t * L;
     if (start64 >= M) return;
     uint32_t start = (uint32_t)start64;
     uint32_t end = (M - start > L) ? start + L : M;
+    dg_mbar_init(bar[0], 1);
+    dg_mbar_init(bar[1], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    uint32_t ent = __ldg(&entries[start]);
+    dg_bulk_fetch(stage[0], &bases[ent & 0x7fffffffu], REC, bar[0]);
+    uint32_t ent1 = (start + 1 < end) ? __ldg(&entries[start + 1]) : 0;
     // bucket containing `start`: largest b with off[b] <= start  (and off[b+1] > start)
     uint32_t lo = 0, hi = nb;            // invariant off[lo] <= start < off[hi]
     while (hi - lo > 1) {
@@ -163,16 +205,24 @@ __global__ void __launch_bounds__(128, (sizeof(F) > 48 ? 2 : 3)) k_accumulate(co
     XYZZ<F> acc = xyzz_inf<F>();
     bool first = true;
     for (uint32_t e = start; e < end; e++) {
+        const uint32_t k = e - start, buf = k & 1;
+        uint32_t ent2 = 0;
+        if (e + 1 < end) {                                   // prefetch the next point into the other buffer
+            dg_bulk_fetch(stage[buf ^ 1], &bases[ent1 & 0x7fffffffu], REC, bar[buf ^ 1]);
+            if (e + 2 < end) ent2 = __ldg(&entries[e + 2]);
+        }
         if (e == bend) {
             if (first) xyzz_store(&head[t], acc); else xyzz_store(&buckets[b], acc);
             first = false;
             acc = xyzz_inf<F>();
             do { b++; bend = off[b + 1]; } while (bend <= e);
         }
-        uint32_t ent = __ldg(&entries[e]);
-        Affine<F> p = aff_load<F>(&bases[ent & 0x7fffffffu]);
+        dg_mbar_wait(bar[buf], (k >> 1) & 1);
+        Affine<F> p = {fload_rw<F>(stage[buf]), fload_rw<F>(stage[buf] + sizeof(F))};
         p.y = fcneg(p.y, (ent >> 31) != 0);
         acc = xyzz_madd(acc, p);
+        ent = ent1;
+        ent1 = ent2;
     }
     if (first) xyzz_store(&head[t], acc); else xyzz_store(&tail[t], acc);
 }
