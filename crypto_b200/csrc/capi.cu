@@ -188,6 +188,7 @@ int32_t dg_shutdown(void) {
     cudaDeviceSynchronize();
     for (auto &kv : c.handles) cudaFree(kv.second.dev);
     c.handles.clear();
+    ntt_release_plans();
     ThreadState &t = tls();
     t.arena.release();
     c.inited = false;

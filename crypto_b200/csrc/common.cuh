@@ -92,6 +92,7 @@ int32_t msm_run_g1(const void *bases_dev, const void *scalars_dev, size_t n, voi
                    uint32_t *err_flag, cudaStream_t s, MsmPre pre);
 int32_t msm_run_g2(const void *bases_dev, const void *scalars_dev, size_t n, void *out_jac_dev, char *scratch,
                    uint32_t *err_flag, cudaStream_t s, MsmPre pre);
+void ntt_release_plans();                                                                  // ntt.cu
 int32_t fr_into_bigint_device(const void *in, void *out, size_t n, cudaStream_t s);   // ntt.cu
 int32_t bases_precompute_g1(HandleRec &rec, int c, cudaStream_t s);
 int32_t bases_precompute_g2(HandleRec &rec, int c, cudaStream_t s);

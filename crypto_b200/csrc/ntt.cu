@@ -166,6 +166,14 @@ int32_t fr_into_bigint_device(const void *in, void *out, size_t n, cudaStream_t 
     return DG_OK;
 }
 
+void ntt_release_plans() {
+    for (auto &kv : plans()) {
+        cudaFree(kv.second.tw_fwd); cudaFree(kv.second.tw_inv); cudaFree(kv.second.scale_fwd); cudaFree(kv.second.scale_inv);
+        cudaFree(kv.second.consts);
+    }
+    plans().clear();
+}
+
 static int32_t get_plan(uint32_t logn, cudaStream_t s, NttPlan &out) {
     std::lock_guard<std::mutex> lk(ctx().mu);
     auto it = plans().find(logn);
