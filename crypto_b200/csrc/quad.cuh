@@ -110,6 +110,7 @@ template <class F> __device__ __noinline__ void quad_add(QuadWS<F> &w, int D, in
     __syncwarp(q.mask);
     F P = fsub(T[1], T[0]), R = fsub(T[3], T[2]);
     if (fis_zero(P)) {                                     // quad-uniform, rare
+        __syncwarp(q.mask);                                // every lane has read T[0..3] before quad_dbl reuses them
         if (fis_zero(R)) {
             quad_dbl(w, D, A, q);
         } else {

@@ -1,0 +1,33 @@
+#!/bin/bash
+# compute-sanitizer passes over small configurations (race detection / sanitizers).
+# usage: tools/sanitize.sh  (on a GPU box); logs under gpurun_out/
+mkdir -p gpurun_out
+SAN=/usr/local/cuda/bin/compute-sanitizer
+cat > /tmp/san_small.py <<'PY'
+import sys, os
+sys.path.insert(0, os.getcwd())
+import numpy as np
+from oracle import cref
+from crypto_b200 import lib
+lib.init(0)
+n = 600
+ks = cref.random_scalars(n, 1); ss = cref.random_scalars(n, 2)
+bases = cref.g1_generator_muls(ks)
+ok = bytes(cref.normalize_batch_g1(lib.msm(bases, ss))) == bytes(cref.normalize_batch_g1(cref.msm_g1(bases, ss)))
+hb = lib.Bases(bases).precompute(10)
+ok &= bytes(cref.normalize_batch_g1(lib.msm(hb, ss))) == bytes(cref.normalize_batch_g1(cref.msm_g1(bases, ss)))
+hb.free()
+b2 = cref.g2_generator_muls(ks[:32 * 40])
+ok &= bytes(cref.normalize_batch_g2(lib.msm(b2, ss[:32 * 40], g2=True))) == bytes(cref.normalize_batch_g2(cref.msm_g2(b2, ss[:32 * 40])))
+t = lib.FixedBaseTable(bases[:96], 40)
+ok &= bytes(cref.normalize_batch_g1(t.mul_many(ss[:32 * 8]))) == bytes(cref.normalize_batch_g1(cref.batch_mul_g1(np.tile(bases[:96], 8), ss[:32 * 8])))
+t.free()
+ok &= bytes(lib.multi_pairing(bases[:96 * 2], b2[:192 * 2])) == bytes(cref.multi_pairing(bases[:96 * 2], b2[:192 * 2]))
+d = cref.random_scalars(1 << 10, 5)
+ok &= bytes(lib.fr_ntt(d, 10, False, True)) == bytes(cref.fr_ntt(d, 10, False, True))
+print('sanitizer workload ok =', bool(ok))
+PY
+for tool in memcheck racecheck; do
+  $SAN --tool $tool --error-exitcode 1 python /tmp/san_small.py > gpurun_out/sanitizer_$tool.log 2>&1
+  echo "$tool exit=$?"; tail -4 gpurun_out/sanitizer_$tool.log
+done
