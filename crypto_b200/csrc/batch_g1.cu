@@ -13,7 +13,8 @@ __global__ void __launch_bounds__(128) k_dbg_fp_op(int op, const Fp *a, const Fp
         case 2: r = fp_sub(x, y); break;
         case 3: r = fp_sqr(x); break;
         case 4: r = fp_neg(x); break;
-        case 5: r = fp_inv(x); break;
+        case 5: r = fp_inv(x); break;            // Fermat a^(p-2)
+        case 6: r = fp_inv_binary(x); break;     // binary extended Euclid (the one the kernels use)
         default: r = fp_zero();
     }
     fp_store(&out[i], r);

@@ -20,6 +20,7 @@
 // is bit-identical to arkworks', not only the pairing.
 #include "common.cuh"
 #include "ec.cuh"
+#include "fp_inv.cuh"
 
 namespace dg {
 
@@ -104,6 +105,58 @@ __device__ void f12_mul(Engine &e, F12 *C, const F12 *A, const F12 *B) {
     __syncthreads();
 }
 
+// C = A^2 for A in the cyclotomic subgroup (every value after the easy part of the final
+// exponentiation, and every GT element): Granger-Scott squaring.  With Fp4 = Fp2[t]/(t^2 - xi),
+// t = w^3, write A = X + Y w + Z w^2, X = (a0, a3), Y = (a1, a4), Z = (a2, a5); then
+//   A^2 = (3 X^2 - 2 conj X) + (3 t Z^2 + 2 conj Y) w + (3 Y^2 - 2 conj Z) w^2
+// (checked against the generic square in the big-integer oracle).  Nine Fp2 squarings = 18 Fp
+// multiplications in ONE wave of 18 lanes, then 12 lanes recombine.  C may alias A.
+__device__ void f12_cyc_sqr(Engine &e, F12 *C, const F12 *A) {
+    int tid = threadIdx.x;
+    if (tid < 18) {
+        // lane = 2 s + h;  s = 3 m + j:  Fp4 number m (0: X, 1: Y, 2: Z), j = 0: x0, 1: x1, 2: x0 + x1
+        int sidx = tid >> 1, h = tid & 1, m = sidx / 3, j = sidx - 3 * m;
+        const Fp *x0 = &A->c[widx(m)], *x1 = &A->c[widx(m + 3)];
+        Fp v0, v1;
+        if (j == 0) { v0 = x0[0]; v1 = x0[1]; }
+        else if (j == 1) { v0 = x1[0]; v1 = x1[1]; }
+        else { v0 = fp_add(x0[0], x1[0]); v1 = fp_add(x0[1], x1[1]); }
+        // complex squaring (v0 + v1 u)^2 = (v0 + v1)(v0 - v1) + 2 v0 v1 u : lane h takes one product
+        Fp a = h ? v0 : fp_add(v0, v1), b = h ? v1 : fp_sub(v0, v1);
+        e.prod[tid] = fp_mul_smem(&a, &b);
+    }
+    __syncthreads();
+    if (tid < 12) {
+        int k = tid >> 1, comp = tid & 1;
+        // component `c` of the Fp2 square number s:  c = 0: prod[2s],  c = 1: 2 * prod[2s + 1]
+        auto S = [&](int sq, int c) -> Fp { return c ? fp_dbl(e.prod[2 * sq + 1]) : e.prod[2 * sq]; };
+        // Fp4 square of number m:  part 0 = S0 + xi S1,  part 1 = S2 - S0 - S1
+        auto part0 = [&](int m, int c) -> Fp {
+            Fp s1a = S(3 * m + 1, 0), s1b = S(3 * m + 1, 1);
+            Fp x = c ? fp_add(s1a, s1b) : fp_sub(s1a, s1b);               // (xi S1).c
+            return fp_add(S(3 * m, c), x);
+        };
+        auto part1 = [&](int m, int c) -> Fp { return fp_sub(fp_sub(S(3 * m + 2, c), S(3 * m, c)), S(3 * m + 1, c)); };
+        Fp v;
+        bool plus;
+        switch (k) {
+            case 0: v = part0(0, comp); plus = false; break;               // 3 X^2.0 - 2 a0
+            case 3: v = part1(0, comp); plus = true; break;                // 3 X^2.1 + 2 a3
+            case 2: v = part0(1, comp); plus = false; break;               // 3 Y^2.0 - 2 a2
+            case 5: v = part1(1, comp); plus = true; break;                // 3 Y^2.1 + 2 a5
+            case 4: v = part0(2, comp); plus = false; break;               // 3 Z^2.0 - 2 a4
+            default: {                                                     // k = 1: 3 xi Z^2.1 + 2 a1
+                Fp p0 = part1(2, 0), p1 = part1(2, 1);
+                v = comp ? fp_add(p0, p1) : fp_sub(p0, p1);
+                plus = true;
+            }
+        }
+        Fp three = fp_add(fp_dbl(v), v), two_a = fp_dbl(A->c[widx(k) + comp]);
+        C->c[widx(k) + comp] = plus ? fp_add(three, two_a) : fp_sub(three, two_a);
+    }
+    __syncthreads();
+}
+
 __device__ void f12_copy(F12 *d, const F12 *s) {
     int tid = threadIdx.x;
     if (tid < 12) d->c[tid] = s->c[tid];
@@ -174,7 +227,7 @@ __device__ void f12_inv(Engine &e, F12 *d, const F12 *s, F12 *t0, F12 *t1, F12 *
     f12_mul(e, t1, t1, d);           // Norm in Fp2: only the w^0 coefficient is non-zero
     if (tid == 0) {
         Fp x = t1->c[0], y = t1->c[1];
-        Fp n = fp_inv_serial(fp_add(fp_mul(x, x), fp_mul(y, y)));
+        Fp n = fp_inv_binary(fp_add(fp_mul(x, x), fp_mul(y, y)));
         t1->c[0] = fp_mul(x, n);
         t1->c[1] = fp_neg(fp_mul(y, n));
     }
@@ -186,7 +239,7 @@ __device__ void f12_inv(Engine &e, F12 *d, const F12 *s, F12 *t0, F12 *t1, F12 *
 __device__ void f12_exp_by_x(Engine &e, F12 *d, const F12 *s) {
     f12_copy(d, s);                                   // top bit (63) of |x|
     for (int i = 62; i >= 0; i--) {
-        f12_mul(e, d, d, d);
+        f12_cyc_sqr(e, d, d);                          // operands of exp_by_x are cyclotomic
         if ((BLS_X_ABS >> i) & 1) f12_mul(e, d, d, s);
     }
     f12_conj(d, d);
@@ -200,7 +253,7 @@ __device__ void f12_final_exp(Engine &e, F12 *r, F12 *f1, F12 *f2, F12 *y0, F12 
     f12_copy(f2, r);
     f12_frobenius(e, r, r, 2);
     f12_mul(e, r, r, f2);                  // ^(p^2+1)
-    f12_mul(e, y0, r, r);                  // y0 = r^2
+    f12_cyc_sqr(e, y0, r);                 // y0 = r^2 (ark: cyclotomic_square)
     f12_exp_by_x(e, y1, r);
     f12_conj(y2, r);
     f12_mul(e, y1, y1, y2);
@@ -502,8 +555,9 @@ __global__ void __launch_bounds__(PAIR_THREADS) k_f12_mul_or_pow(const F12 *a, c
         f12_mul(S.e, &S.f, &S.t[0], &S.t[1]);
     } else {
         f12_set_one(&S.f);
+        // GT elements are cyclotomic, so the squarings use Granger-Scott; the accumulator starts at 1
         for (int i = 255; i >= 0; i--) {
-            f12_mul(S.e, &S.f, &S.f, &S.f);
+            f12_cyc_sqr(S.e, &S.f, &S.f);
             if ((scalar[i >> 5] >> (i & 31)) & 1) f12_mul(S.e, &S.f, &S.f, &S.t[0]);
         }
     }

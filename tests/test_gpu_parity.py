@@ -36,10 +36,12 @@ def test_fp_ops_vs_bigint(dg, op):
     assert out == exp
 
 
-def test_fp_inverse(dg):
-    xs = [1, 2, o.P - 1, 0x1234567890ABCDEF, 0]
+@pytest.mark.parametrize('op', [5, 6])          # 5: Fermat, 6: binary extended Euclid
+def test_fp_inverse(dg, op):
+    rng = np.random.default_rng(7)
+    xs = [1, 2, o.P - 1, 0x1234567890ABCDEF, 0, 3, (o.P + 1) // 2] + [int.from_bytes(rng.bytes(48), 'little') % o.P for _ in range(200)]
     a = b''.join(o.fp_to_mont_bytes(x) for x in xs)
-    out = bytes(dg.dbg_fp_op(5, a, a))
+    out = bytes(dg.dbg_fp_op(op, a, a))
     exp = b''.join(o.fp_to_mont_bytes(pow(x, o.P - 2, o.P)) for x in xs)
     assert out == exp
 
