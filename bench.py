@@ -311,6 +311,13 @@ def run_ours(args, rank, world, local_rank):
         line['int_roofline'] = {'bound': 'imad', 'achieved': macs / (acc_ms * 1e-3), 'peak': imad_peak, 'unit': 'MAC/s',
                                 'frac': macs / (acc_ms * 1e-3) / imad_peak,
                                 'peak_source': 'profiles/int_peak_r01.json imad_lo (measured on this pool)'}
+    fp = load_profile_json('fpmul_peak_r01.json') or {}
+    mult_peak = fp.get('fp_mul_12x32_carry_chain_mults_per_s')
+    if mult_peak and acc_ms:
+        mults = n * nwin * 10.0                     # 8M + 2S per mixed addition, nwin additions per term
+        line['mult_roofline'] = {'bound': 'fp-multiplier issue', 'achieved': mults / (acc_ms * 1e-3), 'peak': mult_peak,
+                                 'unit': 'Fp mult/s', 'frac': mults / (acc_ms * 1e-3) / mult_peak,
+                                 'peak_source': 'profiles/fpmul_peak_r01.json (tools/fpmul_bench.cu, measured on this pool)'}
     if world == 1 and not args.no_cpu:
         cores = host_cores()
         os.environ.setdefault('OMP_NUM_THREADS', str(cores))
