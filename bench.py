@@ -11,13 +11,13 @@ all-gathered (NCCL, 144 B per rank) and folded on the GPU under the group law.
 `value`   : terms/s with scalars and bases already resident in HBM (dg_msm_g1_handle_device).
             Bases live behind a handle as in the reference's workloads (proving keys / signature
             parameters are fixed across calls) with the 2^(20k)-multiples table built
-            once at upload (dg_bases_precompute, 13 x the base memory).  `value_plain_bases` is the
+            once at upload (dg_bases_precompute, 16 x the base memory at 2^20).  `value_plain_bases` is the
             same MSM through dg_msm_g1_device on the raw 96-byte bases with nothing precomputed.
 `e2e`     : terms/s through the host C-ABI call dg_msm_g1 with the scalars in pinned host memory
             copied every step and the 144-byte result read back every step (same handle);
             `e2e_plain_bases` likewise without the precomputed table.
 --total-logn T switches to strong scaling: one 2^T-term MSM split over the ranks.
-`roofline`: the dominant kernel (k_accumulate) against the measured HBM peak, algorithmic bytes
+`roofline`: the dominant kernel (round 0 of the batch-affine stage, else k_accumulate) against the measured HBM peak, algorithmic bytes
             128 B/term; `int_roofline` is the integer-pipe reading of the same launch.
 `cpu_baseline`: the oracle's C restatement of the arkworks rayon algorithm on the host cores.
 """
@@ -278,11 +278,21 @@ def run_ours(args, rank, world, local_rank):
         hbm_peak, peak_src = 6650.0, 'fallback (B200_PROFILING.md)'
     alg_bytes = 128.0 * n                                   # 32 B scalar + 96 B affine base per term
     achieved = alg_bytes / (acc_ms * 1e-3) / 1e9 if acc_ms else None
-    ncu = load_profile_json('ncu_accumulate.json') or {}
     ip = load_profile_json('int_peak_r01.json') or {}
     imad_peak = (ip.get('imad_lo') or {}).get('ops_per_s')
-    pre_c = args.precompute_window if args.precompute_window else (20 if n >= (1 << 18) else 16)
+    pre_c = args.precompute_window if args.precompute_window else (20 if n >= (1 << 21) else 16)   # dg_bases_precompute default
     nwin = (256 + pre_c - 1) // pre_c
+    _, rounds = lib.msm_plan(n, precomputed_c=pre_c)
+    # The dominant kernel: with batch-affine rounds it is round 0 (k_affine_round<Fp, gather>), which visits every
+    # (scalar digit, base) entry once and performs half of them as affine additions; without rounds k_accumulate.
+    if rounds:
+        dom_kernel = 'k_affine_round<Fp, gather> (round 0 of %d)' % rounds
+        ncu = load_profile_json('ncu_affine_round.json') or {}
+        adds, mults_per_add = n * nwin / 2.0, 6.0          # 5M + 1S per affine addition incl. the shared inversion
+    else:
+        dom_kernel = 'k_accumulate<Fp>'
+        ncu = load_profile_json('ncu_accumulate.json') or {}
+        adds, mults_per_add = float(n * nwin), 10.0        # 8M + 2S per XYZZ mixed addition
     line = {
         'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
         'ms_per_step': total_ms / args.steps, 'higher_is_better': True, 'scaling': 'strong' if strong else 'weak',
@@ -298,23 +308,23 @@ def run_ours(args, rank, world, local_rank):
                 'note': 'dg_msm_g1 host call; scalars from pinned host memory every step; bases resident (handle)'},
         'e2e_plain_bases': e2e_plain,
         'gpu_launches': int(launches),
-        'roofline': {'bound': 'hbm', 'kernel': 'k_accumulate<Fp>', 'achieved': achieved, 'peak': hbm_peak, 'unit': 'GB/s',
+        'roofline': {'bound': 'hbm', 'kernel': dom_kernel, 'achieved': achieved, 'peak': hbm_peak, 'unit': 'GB/s',
                      'frac': (achieved / hbm_peak) if achieved else None, 'traffic': ncu.get('dram_bytes_per_launch'),
                      'peak_source': peak_src, 'kernel_ms': acc_ms, 'launches_timed': acc_cnt,
                      'algorithmic_bytes_per_launch': alg_bytes,
                      'note': 'integer-issue bound, not HBM bound (SURVEY 8d): see int_roofline'},
     }
     if imad_peak and acc_ms and nwin:
-        # 32x32 multiply-accumulates the accumulation algorithmically needs: nwin mixed adds/term,
-        # 10 Fp mults each, 2*12^2 MACs per Montgomery mult
-        macs = n * nwin * 10 * 288.0
+        # 32x32 multiply-accumulates the dominant launch algorithmically needs: its additions x Fp mults per
+        # addition x 2*12^2 MACs per Montgomery mult
+        macs = adds * mults_per_add * 288.0
         line['int_roofline'] = {'bound': 'imad', 'achieved': macs / (acc_ms * 1e-3), 'peak': imad_peak, 'unit': 'MAC/s',
                                 'frac': macs / (acc_ms * 1e-3) / imad_peak,
                                 'peak_source': 'profiles/int_peak_r01.json imad_lo (measured on this pool)'}
     fp = load_profile_json('fpmul_peak_r01.json') or {}
     mult_peak = fp.get('fp_mul_12x32_carry_chain_mults_per_s')
     if mult_peak and acc_ms:
-        mults = n * nwin * 10.0                     # 8M + 2S per mixed addition, nwin additions per term
+        mults = adds * mults_per_add
         line['mult_roofline'] = {'bound': 'fp-multiplier issue', 'achieved': mults / (acc_ms * 1e-3), 'peak': mult_peak,
                                  'unit': 'Fp mult/s', 'frac': mults / (acc_ms * 1e-3) / mult_peak,
                                  'peak_source': 'profiles/fpmul_peak_r01.json (tools/fpmul_bench.cu, measured on this pool)'}

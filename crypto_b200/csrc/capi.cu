@@ -1,5 +1,6 @@
 // C ABI of libdockgpu.so (include/dockgpu.h): context, handles, host<->device staging and the
 // MSM entry points.  Everything here is plumbing around the kernels; no arithmetic on the host.
+#include <cstdlib>
 #include <cstring>
 #include "common.cuh"
 #include "ec.cuh"
@@ -175,6 +176,14 @@ int32_t dg_init(int32_t device) {
     cudaDeviceProp prop;
     DG_CUDA(cudaGetDeviceProperties(&prop, device));
     if (prop.major < 10) return fail(DG_ERR_CUDA, "libdockgpu is built for sm_100a (B200) only");
+    // The hot kernels gather 96-byte records at random from tables far larger than L2; ask for the
+    // smallest DRAM->L2 fetch granularity so a miss does not drag the whole 128-byte line in.
+    {
+        size_t gran = 32;
+        if (const char *e = getenv("DG_L2_FETCH_GRANULARITY")) gran = (size_t)atoi(e);
+        if (gran) cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, gran);
+        cudaGetLastError();
+    }
     c.device = device;
     c.sm_count = prop.multiProcessorCount;
     c.inited = true;
@@ -247,7 +256,7 @@ int32_t dg_bases_precompute(uint64_t handle, int32_t c) {
     auto it = ctx().handles.find(handle);
     if (it == ctx().handles.end() || (it->second.kind != HandleRec::BASES_G1 && it->second.kind != HandleRec::BASES_G2))
         return fail(DG_ERR_BAD_ARG, "bases_precompute: bad handle");
-    if (c == 0) c = it->second.n >= (1u << 18) ? 20 : 16;
+    if (c == 0) c = it->second.n >= (1u << 21) ? 20 : 16;     // measured with the batch-affine stage (tools/sweep_rounds.py)
     DG_CUDA(cudaDeviceSynchronize());
     return it->second.kind == HandleRec::BASES_G2 ? bases_precompute_g2(it->second, c, tls().stream)
                                                   : bases_precompute_g1(it->second, c, tls().stream);
@@ -276,6 +285,28 @@ int32_t dg_prof_read_accumulate(double *mean_ms, int32_t *count) {
 int32_t dg_msm_set_window(int32_t c) {
     if (c < 0 || c == 1 || c > 24) return fail(DG_ERR_BAD_ARG, "msm_set_window: c must be 0 or in [2, 24]");
     ctx().msm_window_override.store(c);
+    return DG_OK;
+}
+
+int32_t dg_msm_set_affine_rounds(int32_t rounds) {
+    if (rounds < -1 || rounds > 10) return fail(DG_ERR_BAD_ARG, "msm_set_affine_rounds: rounds must be -1 (automatic) or in [0, 10]");
+    ctx().msm_rounds_override.store(rounds);
+    return DG_OK;
+}
+int32_t dg_dbg_set_tunable(int32_t id, int32_t value) {
+    if (id < 0 || id >= 8) return fail(DG_ERR_BAD_ARG, "dbg_set_tunable: id out of range");
+    ctx().tunable[id].store(value);
+    return DG_OK;
+}
+int32_t dg_msm_plan(size_t n, int32_t is_g2, int32_t precomputed_window_bits, int32_t *window_bits, int32_t *affine_rounds) {
+    int32_t rc = check_init();
+    if (rc) return rc;
+    if (!window_bits || !affine_rounds) return fail(DG_ERR_BAD_ARG, "msm_plan: null pointer");
+    MsmPre pre = {precomputed_window_bits, precomputed_window_bits ? (uint32_t)n : 0u};
+    int c = 0, r = 0;
+    if (is_g2) msm_plan_g2(n, pre, &c, &r); else msm_plan_g1(n, pre, &c, &r);
+    *window_bits = c;
+    *affine_rounds = r;
     return DG_OK;
 }
 

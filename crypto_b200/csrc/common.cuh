@@ -29,6 +29,8 @@ struct Context {
     uint64_t next_handle = 1;
     std::atomic<uint64_t> launches{0};
     std::atomic<int> msm_window_override{0};
+    std::atomic<int> msm_rounds_override{-1};   // batch-affine rounds: -1 = automatic
+    std::atomic<int> tunable[8] = {};             // dg_dbg_set_tunable: 0 = batch-affine waves per round (0 -> 1)
     // optional per-kernel timing of the dominant kernel (bench.py roofline): event pairs recorded
     // on the launching stream around every k_accumulate launch while enabled
     std::atomic<int> prof_enabled{0};
@@ -88,6 +90,8 @@ static inline unsigned div_up(size_t a, size_t b) { return (unsigned)((a + b - 1
 struct MsmPre { int c; uint32_t row_stride; };
 size_t msm_scratch_bytes_g1(size_t n, MsmPre pre);
 size_t msm_scratch_bytes_g2(size_t n, MsmPre pre);
+void msm_plan_g1(size_t n, MsmPre pre, int *c, int *rounds);
+void msm_plan_g2(size_t n, MsmPre pre, int *c, int *rounds);
 int32_t msm_run_g1(const void *bases_dev, const void *scalars_dev, size_t n, void *out_jac_dev, char *scratch,
                    uint32_t *err_flag, cudaStream_t s, MsmPre pre);
 int32_t msm_run_g2(const void *bases_dev, const void *scalars_dev, size_t n, void *out_jac_dev, char *scratch,

@@ -3,6 +3,11 @@
 #include "msm_host.cuh"
 namespace dg {
 size_t msm_scratch_bytes_g2(size_t n, MsmPre pre) { return msm_layout<Fp2>(n, pre).total; }
+void msm_plan_g2(size_t n, MsmPre pre, int *c, int *rounds) {
+    MsmLayout m = msm_layout<Fp2>(n, pre);
+    *c = m.g.c;
+    *rounds = m.R;
+}
 int32_t msm_run_g2(const void *bases_dev, const void *scalars_dev, size_t n, void *out_jac_dev, char *scratch,
                    uint32_t *err_flag, cudaStream_t s, MsmPre pre) {
     return msm_run<Fp2>(bases_dev, scalars_dev, n, out_jac_dev, scratch, err_flag, s, pre);

@@ -3,6 +3,7 @@
 #pragma once
 #include "common.cuh"
 #include "msm_kernels.cuh"
+#include "msm_affine.cuh"
 
 namespace dg {
 
@@ -29,22 +30,56 @@ static inline MsmGeom msm_geometry(size_t n, MsmPre pre) {
     return g;
 }
 
+#define DG_BA_MAX_ROUNDS 10
 struct MsmLayout {
     MsmGeom g;
     uint32_t L, nchunks, ngroups1;
     size_t o_hist, o_off, o_cursor, o_bsums, o_entries, o_buckets, o_head, o_tail, o_long, o_red[4], total;
+    // batch-affine pre-reduction (msm_affine.cuh): R rounds, round r turns <= mb[r] points into <= mb[r + 1]
+    int R;
+    uint64_t mb[DG_BA_MAX_ROUNDS + 1];
+    uint32_t K[DG_BA_MAX_ROUNDS], ctas[DG_BA_MAX_ROUNDS];
+    size_t o_cnt, cnt_stride, o_offr[DG_BA_MAX_ROUNDS], o_aff[2], o_pre, o_rbsums, rbs_stride;
 };
+
+// Rounds of batch-affine halving before the XYZZ accumulation: each round costs ~6.3 instead of 10
+// multiplications per addition but has a fixed cost (launch, one inversion per CTA batch), so it
+// pays while the buckets still hold several points each.
+static inline int msm_affine_rounds(size_t n, const MsmGeom &g) {
+    int ov = ctx().msm_rounds_override.load();
+    if (ov >= 0) return ov > DG_BA_MAX_ROUNDS ? DG_BA_MAX_ROUNDS : ov;
+    // measured (tools/sweep_rounds.py): a round pays while the buckets still hold >= 6 points and it
+    // has >= 2^20 additions to spread over the grid
+    double entries = (double)n * g.ndig, load = entries / (double)g.nb;     // average points per bucket
+    int r = 0;
+    while (r < DG_BA_MAX_ROUNDS && load >= 6.0 && entries * 0.5 >= 1048576.0) { load *= 0.5; entries *= 0.5; r++; }
+    return r;
+}
 
 template <class F> static inline MsmLayout msm_layout(size_t n, MsmPre pre) {
     MsmLayout m;
     m.g = msm_geometry(n, pre);
     size_t max_entries = n * (size_t)m.g.ndig;
+    m.R = msm_affine_rounds(n, m.g);
+    m.mb[0] = max_entries;
+    for (int r = 0; r < m.R; r++) m.mb[r + 1] = (m.mb[r] + m.g.nb) / 2 + 1;     // sum_b ceil(n_b / 2) <= (M + nb) / 2
+    int waves = ctx().tunable[0].load();
+    if (waves < 1) waves = 1;
+    const size_t ba_threads = (size_t)ctx().sm_count * (sizeof(F) > 48 ? 2 : 4) * DG_BA_THREADS * waves;   // resident waves per round
+    for (int r = 0; r < m.R; r++) {
+        size_t k = (m.mb[r + 1] + ba_threads - 1) / ba_threads;
+        if (k < 16) k = 16;                     // one inversion per CTA batch of 128 x K additions
+        if (k > 128) k = 128;
+        m.K[r] = (uint32_t)k;
+        m.ctas[r] = (uint32_t)((m.mb[r + 1] + k * DG_BA_THREADS - 1) / (k * DG_BA_THREADS));
+    }
+    const size_t acc_entries = m.mb[m.R];                                         // what k_accumulate folds
     size_t threads_target = (size_t)ctx().sm_count * 384 * 4;
-    size_t L = (max_entries + threads_target - 1) / threads_target;
+    size_t L = (acc_entries + threads_target - 1) / threads_target;
     if (L < 8) L = 8;
     if (L > 512) L = 512;
     m.L = (uint32_t)L;
-    m.nchunks = (uint32_t)((max_entries + L - 1) / L);
+    m.nchunks = (uint32_t)((acc_entries + L - 1) / L);
     if (m.nchunks == 0) m.nchunks = 1;
     int log_g1 = m.g.nbw >= 4096 ? 4 : 3;
     m.ngroups1 = (m.g.nbw + (1u << log_g1) - 1) >> log_g1;
@@ -60,6 +95,23 @@ template <class F> static inline MsmLayout msm_layout(size_t n, MsmPre pre) {
     m.o_tail = take(sizeof(XYZZ<F>) * m.nchunks);
     m.o_long = take(sizeof(uint32_t) * (m.nchunks / DG_LONG_PIECES + 64));     // [0] = count, list from [16]
     for (int k = 0; k < 4; k++) m.o_red[k] = take(sizeof(XYZZ<F>) * (size_t)m.g.nwin * m.ngroups1);
+    m.o_cnt = m.cnt_stride = m.o_pre = m.o_rbsums = m.rbs_stride = 0;
+    m.o_aff[0] = m.o_aff[1] = 0;
+    if (m.R) {
+        m.cnt_stride = Arena::pad(sizeof(uint32_t) * m.g.nb) / sizeof(uint32_t);
+        m.o_cnt = take(sizeof(uint32_t) * m.cnt_stride * m.R);
+        for (int r = 0; r < m.R; r++) m.o_offr[r] = take(sizeof(uint32_t) * ((size_t)m.g.nb + 1));      // equal sizes: constant stride
+        m.rbs_stride = Arena::pad(sizeof(uint32_t) * (m.g.nb / DG_SCAN_ITEMS + 2)) / sizeof(uint32_t);
+        m.o_rbsums = take(sizeof(uint32_t) * m.rbs_stride * m.R);
+        m.o_aff[0] = take(sizeof(Affine<F>) * m.mb[1]);                           // A_1, A_3, A_5
+        if (m.R > 1) m.o_aff[1] = take(sizeof(Affine<F>) * m.mb[2]);              // A_2, A_4, A_6
+        size_t pre = 0;
+        for (int r = 0; r < m.R; r++) {
+            size_t b = (size_t)m.K[r] * m.ctas[r] * DG_BA_THREADS * sizeof(F);
+            if (b > pre) pre = b;
+        }
+        m.o_pre = take(pre);
+    }
     m.total = o;
     return m;
 }
@@ -99,30 +151,70 @@ static int32_t msm_run(const void *bases_dev, const void *scalars_dev, size_t n,
     DG_LAUNCH(k_scan_add, sb, 1024, 0, s, off, bsums, hist, g.nb, cursor);
     DG_LAUNCH(k_digits<1>, gd, 256, 0, s, (const uint32_t *)scalars_dev, (uint32_t)n, g, cursor, entries, err_flag);
 
+    // stage 4a: R rounds of batch-affine pairwise halving (msm_affine.cuh)
+    const uint32_t *acc_off = off;
+    const Affine<F> *acc_points = (const Affine<F> *)bases_dev;
     cudaEvent_t pe0 = nullptr, pe1 = nullptr;
     if (ctx().prof_enabled.load()) {
         DG_CUDA(cudaEventCreate(&pe0));
         DG_CUDA(cudaEventCreate(&pe1));
-        DG_CUDA(cudaEventRecord(pe0, s));
     }
+    if (m.R) {
+        uint32_t *cnt = (uint32_t *)(scratch + m.o_cnt);
+        DG_LAUNCH(k_round_counts, div_up(g.nb, 256), 256, 0, s, off, g.nb, m.R, cnt, m.cnt_stride);
+        {                                                      // all R offset arrays in three launches (blockIdx.y = round)
+            uint32_t *offr0 = (uint32_t *)(scratch + m.o_offr[0]), *bs = (uint32_t *)(scratch + m.o_rbsums);
+            const size_t ostr = m.R > 1 ? (m.o_offr[1] - m.o_offr[0]) / sizeof(uint32_t) : 0, bstr = m.rbs_stride;
+            DG_LAUNCH(k_scan_blocks, dim3(sb, m.R), 1024, 0, s, cnt, offr0, bs, g.nb, m.cnt_stride, ostr, bstr);
+            DG_LAUNCH(k_scan_sums, dim3(1, m.R), 1024, 0, s, bs, sb, bstr);
+            DG_LAUNCH(k_scan_add, dim3(sb, m.R), 1024, 0, s, offr0, bs, cnt, g.nb, (uint32_t *)nullptr, m.cnt_stride, ostr, bstr);
+        }
+        uint4 *pre_scratch = (uint4 *)(scratch + m.o_pre);
+        for (int r = 0; r < m.R; r++) {
+            const uint32_t *off_in = r ? (const uint32_t *)(scratch + m.o_offr[r - 1]) : off;
+            const uint32_t *off_out = (const uint32_t *)(scratch + m.o_offr[r]);
+            Affine<F> *dst = (Affine<F> *)(scratch + m.o_aff[r & 1]);
+            const Affine<F> *src = r ? (const Affine<F> *)(scratch + m.o_aff[(r - 1) & 1]) : (const Affine<F> *)bases_dev;
+            if (r == 0 && pe0) DG_CUDA(cudaEventRecord(pe0, s));
+            {
+                auto kg = k_affine_round<F, true>;
+                auto kd = k_affine_round<F, false>;
+                if (r == 0) DG_LAUNCH(kg, m.ctas[r], DG_BA_THREADS, 0, s, src, entries, off_in, off_out, g.nb, m.K[r], dst, pre_scratch);
+                else DG_LAUNCH(kd, m.ctas[r], DG_BA_THREADS, 0, s, src, (const uint32_t *)nullptr, off_in, off_out, g.nb, m.K[r], dst, pre_scratch);
+            }
+            if (r == 0 && pe0) DG_CUDA(cudaEventRecord(pe1, s));
+        }
+        acc_off = (const uint32_t *)(scratch + m.o_offr[m.R - 1]);
+        acc_points = (const Affine<F> *)(scratch + m.o_aff[(m.R - 1) & 1]);
+    }
+    // stage 4b: XYZZ accumulation of what is left
     {
         static bool smem_opt_in = false;                   // the Fp2 staging buffers exceed the 48 KB default
         if (!smem_opt_in) {
-            DG_CUDA(cudaFuncSetAttribute(k_accumulate<F>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dg_acc_smem_bytes<F>()));
+            DG_CUDA(cudaFuncSetAttribute(k_accumulate<F, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dg_acc_smem_bytes<F>()));
+            DG_CUDA(cudaFuncSetAttribute(k_accumulate<F, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dg_acc_smem_bytes<F>()));
             smem_opt_in = true;
         }
     }
-    DG_LAUNCH(k_accumulate<F>, div_up(m.nchunks, DG_ACC_THREADS), DG_ACC_THREADS, dg_acc_smem_bytes<F>(), s,
-              (const Affine<F> *)bases_dev, entries, off, g.nb, m.L, buckets, head, tail);
+    if (m.R) {
+        auto kfn = k_accumulate<F, true>;
+        DG_LAUNCH(kfn, div_up(m.nchunks, DG_ACC_THREADS), DG_ACC_THREADS, dg_acc_smem_bytes<F>(), s, acc_points,
+                  (const uint32_t *)nullptr, acc_off, g.nb, m.L, buckets, head, tail);
+    } else {
+        if (pe0) DG_CUDA(cudaEventRecord(pe0, s));
+        auto kfn = k_accumulate<F, false>;
+        DG_LAUNCH(kfn, div_up(m.nchunks, DG_ACC_THREADS), DG_ACC_THREADS, dg_acc_smem_bytes<F>(), s, acc_points,
+                  entries, acc_off, g.nb, m.L, buckets, head, tail);
+        if (pe0) DG_CUDA(cudaEventRecord(pe1, s));
+    }
     if (pe0) {
-        DG_CUDA(cudaEventRecord(pe1, s));
         std::lock_guard<std::mutex> lk(ctx().mu);
         ctx().prof_events.emplace_back(pe0, pe1);
     }
     uint32_t *long_count = (uint32_t *)(scratch + m.o_long), *long_list = long_count + 16;
     DG_CUDA(cudaMemsetAsync(long_count, 0, 64, s));
-    DG_LAUNCH(k_bucket_fixup<F>, div_up(g.nb, 128), 128, 0, s, off, g.nb, m.L, buckets, head, tail, long_count, long_list);
-    DG_LAUNCH(k_bucket_fixup_long<F>, 2 * ctx().sm_count, 128, sizeof(XYZZ<F>) * 128, s, off, m.L, buckets, head, tail,
+    DG_LAUNCH(k_bucket_fixup<F>, div_up(g.nb, 128), 128, 0, s, acc_off, g.nb, m.L, buckets, head, tail, long_count, long_list);
+    DG_LAUNCH(k_bucket_fixup_long<F>, 2 * ctx().sm_count, 128, sizeof(XYZZ<F>) * 128, s, acc_off, m.L, buckets, head, tail,
               long_count, long_list);
 
     // multi-level bucket reduction

@@ -71,9 +71,13 @@ __global__ void __launch_bounds__(256) k_digits(const uint32_t *__restrict__ sca
 
 // exclusive scan of `in[0..n)` into `out[0..n]` (out[n] = total); 3 small kernels, 4096 items/block
 #define DG_SCAN_ITEMS 4096
+// blockIdx.y selects one of several independent arrays (the per-round counts of msm_affine.cuh):
+// array y lives at in + y * in_stride, out + y * out_stride, block_sums + y * bs_stride.
 static __global__ void __launch_bounds__(1024) k_scan_blocks(const uint32_t *__restrict__ in, uint32_t *__restrict__ out,
-                                                      uint32_t *__restrict__ block_sums, uint32_t n) {
+                                                      uint32_t *__restrict__ block_sums, uint32_t n, size_t in_stride = 0,
+                                                      size_t out_stride = 0, size_t bs_stride = 0) {
     __shared__ uint32_t warp_tot[32];
+    in += blockIdx.y * in_stride; out += blockIdx.y * out_stride; block_sums += blockIdx.y * bs_stride;
     uint32_t base = blockIdx.x * DG_SCAN_ITEMS + threadIdx.x * 4;
     uint32_t v[4], sum = 0;
 #pragma unroll
@@ -96,9 +100,10 @@ static __global__ void __launch_bounds__(1024) k_scan_blocks(const uint32_t *__r
 #pragma unroll
     for (int k = 0; k < 4; k++) { if (base + k < n) out[base + k] = excl; excl += v[k]; }
 }
-static __global__ void __launch_bounds__(1024) k_scan_sums(uint32_t *block_sums, uint32_t nblocks) {
-    // single block; serial over tiles of 1024
+static __global__ void __launch_bounds__(1024) k_scan_sums(uint32_t *block_sums, uint32_t nblocks, size_t bs_stride = 0) {
+    // single block per array; serial over tiles of 1024
     __shared__ uint32_t warp_tot[32];
+    block_sums += blockIdx.y * bs_stride;
     __shared__ uint32_t running;
     if (threadIdx.x == 0) running = 0;
     __syncthreads();
@@ -125,14 +130,16 @@ static __global__ void __launch_bounds__(1024) k_scan_sums(uint32_t *block_sums,
     }
 }
 static __global__ void __launch_bounds__(1024) k_scan_add(uint32_t *__restrict__ out, const uint32_t *__restrict__ block_sums,
-                                                   const uint32_t *__restrict__ in, uint32_t n, uint32_t *__restrict__ copy) {
+                                                   const uint32_t *__restrict__ in, uint32_t n, uint32_t *__restrict__ copy,
+                                                   size_t in_stride = 0, size_t out_stride = 0, size_t bs_stride = 0) {
+    in += blockIdx.y * in_stride; out += blockIdx.y * out_stride; block_sums += blockIdx.y * bs_stride;
     uint32_t base = blockIdx.x * DG_SCAN_ITEMS + threadIdx.x * 4, add = block_sums[blockIdx.x];
 #pragma unroll
     for (int k = 0; k < 4; k++)
         if (base + k < n) {
             uint32_t v = out[base + k] + add;
             out[base + k] = v;
-            copy[base + k] = v;
+            if (copy) copy[base + k] = v;
             if (base + k == n - 1) out[n] = v + in[n - 1];
         }
 }
@@ -172,7 +179,9 @@ __device__ __forceinline__ void dg_mbar_wait(uint64_t *bar, uint32_t parity) {
 #define DG_ACC_THREADS 128
 template <class F> constexpr size_t dg_acc_smem_bytes() { return (2 * sizeof(Affine<F>) + 16) * DG_ACC_THREADS; }
 
-template <class F>
+// DIRECT: the points are the dense output of the batch-affine rounds (msm_affine.cuh): entry e IS
+// point e, no sign.
+template <class F, bool DIRECT>
 __global__ void __launch_bounds__(DG_ACC_THREADS, (sizeof(F) > 48 ? 2 : 3)) k_accumulate(const Affine<F> *__restrict__ bases, const uint32_t *__restrict__ entries,
                                                        const uint32_t *__restrict__ off, uint32_t nb, uint32_t L,
                                                        XYZZ<F> *__restrict__ buckets, XYZZ<F> *__restrict__ head,
@@ -192,9 +201,10 @@ __global__ void __launch_bounds__(DG_ACC_THREADS, (sizeof(F) > 48 ? 2 : 3)) k_ac
     dg_mbar_init(bar[0], 1);
     dg_mbar_init(bar[1], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    uint32_t ent = __ldg(&entries[start]);
-    dg_bulk_fetch(stage[0], &bases[ent & 0x7fffffffu], REC, bar[0]);
-    uint32_t ent1 = (start + 1 < end) ? __ldg(&entries[start + 1]) : 0;
+    constexpr uint32_t IDX_MASK = DIRECT ? 0xffffffffu : 0x7fffffffu;
+    uint32_t ent = DIRECT ? start : __ldg(&entries[start]);
+    dg_bulk_fetch(stage[0], &bases[ent & IDX_MASK], REC, bar[0]);
+    uint32_t ent1 = (start + 1 < end) ? (DIRECT ? start + 1 : __ldg(&entries[start + 1])) : 0;
     // bucket containing `start`: largest b with off[b] <= start  (and off[b+1] > start)
     uint32_t lo = 0, hi = nb;            // invariant off[lo] <= start < off[hi]
     while (hi - lo > 1) {
@@ -208,8 +218,8 @@ __global__ void __launch_bounds__(DG_ACC_THREADS, (sizeof(F) > 48 ? 2 : 3)) k_ac
         const uint32_t k = e - start, buf = k & 1;
         uint32_t ent2 = 0;
         if (e + 1 < end) {                                   // prefetch the next point into the other buffer
-            dg_bulk_fetch(stage[buf ^ 1], &bases[ent1 & 0x7fffffffu], REC, bar[buf ^ 1]);
-            if (e + 2 < end) ent2 = __ldg(&entries[e + 2]);
+            dg_bulk_fetch(stage[buf ^ 1], &bases[ent1 & IDX_MASK], REC, bar[buf ^ 1]);
+            if (e + 2 < end) ent2 = DIRECT ? e + 2 : __ldg(&entries[e + 2]);
         }
         if (e == bend) {
             if (first) xyzz_store(&head[t], acc); else xyzz_store(&buckets[b], acc);
@@ -219,7 +229,7 @@ __global__ void __launch_bounds__(DG_ACC_THREADS, (sizeof(F) > 48 ? 2 : 3)) k_ac
         }
         dg_mbar_wait(bar[buf], (k >> 1) & 1);
         Affine<F> p = {fload_rw<F>(stage[buf]), fload_rw<F>(stage[buf] + sizeof(F))};
-        p.y = fcneg(p.y, (ent >> 31) != 0);
+        if (!DIRECT) p.y = fcneg(p.y, (ent >> 31) != 0);
         acc = xyzz_madd(acc, p);
         ent = ent1;
         ent1 = ent2;

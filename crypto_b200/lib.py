@@ -20,6 +20,7 @@ EXPORTS = [
     'dg_msm_g1_handle_device', 'dg_msm_g2_handle_device',
     'dg_msm_unchecked_g1', 'dg_msm_unchecked_g2', 'dg_fr_into_bigint',
     'dg_msm_g1', 'dg_msm_g2', 'dg_msm_g1_device', 'dg_msm_g2_device', 'dg_msm_set_window',
+    'dg_msm_set_affine_rounds', 'dg_msm_plan',
     'dg_fixed_base_table_g1', 'dg_fixed_base_table_g2', 'dg_fixed_base_table_info',
     'dg_fixed_base_table_download', 'dg_fixed_base_table_free',
     'dg_fixed_base_mul_many_g1', 'dg_fixed_base_mul_many_g2',
@@ -31,7 +32,7 @@ EXPORTS = [
     'dg_fold_g1', 'dg_fold_g1_device', 'dg_fold_g2',
     'dg_fr_ntt', 'dg_fr_ntt_device', 'dg_qap_h_from_abc',
     'dg_prof_enable', 'dg_prof_read_accumulate',
-    'dg_dbg_fp_op', 'dg_dbg_fr_op',
+    'dg_dbg_fp_op', 'dg_dbg_fr_op', 'dg_dbg_set_tunable',
 ]
 
 
@@ -194,6 +195,20 @@ def prof_read_accumulate():
 
 def msm_set_window(c):
     _check(init().dg_msm_set_window(C.c_int32(c)))
+
+
+def dbg_set_tunable(i, v):
+    _check(init().dg_dbg_set_tunable(C.c_int32(i), C.c_int32(v)))
+
+
+def msm_set_affine_rounds(r):
+    _check(init().dg_msm_set_affine_rounds(C.c_int32(r)))
+
+
+def msm_plan(n, g2=False, precomputed_c=0):
+    c, r = C.c_int32(0), C.c_int32(0)
+    _check(init().dg_msm_plan(C.c_size_t(n), C.c_int32(1 if g2 else 0), C.c_int32(precomputed_c), C.byref(c), C.byref(r)))
+    return c.value, r.value
 
 
 # ---- fixed base ---------------------------------------------------------------------------------

@@ -67,7 +67,7 @@ int32_t dg_bases_free(uint64_t handle);
 /* Optional, for bases that are reused across many MSMs: replaces the resident points by the table
  * { 2^(c*k) * P_i : k < ceil(256/c) } (ceil(256/c) x the memory, built once on the device).  MSMs
  * through this handle then fold every digit position into ONE bucket set: no window-combination
- * doublings and ceil(256/c) x fewer buckets to reduce.  c = 0 picks a default (20 for n >= 2^18).
+ * doublings and ceil(256/c) x fewer buckets to reduce.  c = 0 picks a default (16 below 2^21 points, 20 from there).
  * Results are identical group elements. */
 int32_t dg_bases_precompute(uint64_t handle, int32_t window_bits);
 
@@ -97,6 +97,12 @@ int32_t dg_msm_g1_handle_device(uint64_t bases_handle, const void *scalars_dev, 
 int32_t dg_msm_g2_handle_device(uint64_t bases_handle, const void *scalars_dev, size_t n, void *out_jac_dev, void *stream);
 /* Overrides the automatic window size (0 restores it); for tuning and tests. */
 int32_t dg_msm_set_window(int32_t c);
+/* Overrides the number of batch-affine halving rounds that precede the XYZZ bucket accumulation
+ * (-1 restores the automatic choice, 0 disables the stage); for tuning and tests. */
+int32_t dg_msm_set_affine_rounds(int32_t rounds);
+/* The plan an n-term MSM would run with: window bits and batch-affine rounds (precomputed_window_bits
+ * = the c given to dg_bases_precompute, 0 for plain bases). */
+int32_t dg_msm_plan(size_t n, int32_t is_g2, int32_t precomputed_window_bits, int32_t *window_bits, int32_t *affine_rounds);
 
 /* ---- fixed-base batch multiplication --------------------------------------------------------
  * utils::msm::WindowTable::new(num_multiplications, group_elem) (utils/src/msm.rs:18-30):
@@ -183,6 +189,8 @@ int32_t dg_prof_read_accumulate(double *mean_ms, int32_t *count);
 
 /* ---- test hooks (field arithmetic parity; not part of the reference-facing surface) ---------- */
 int32_t dg_dbg_fp_op(int32_t op, const uint8_t *a, const uint8_t *b, size_t n, uint8_t *out);
+/* internal tuning knobs for sweeps (id 0: resident waves per batch-affine round) */
+int32_t dg_dbg_set_tunable(int32_t id, int32_t value);
 int32_t dg_dbg_fr_op(int32_t op, const uint8_t *a, const uint8_t *b, size_t n, uint8_t *out);
 
 #ifdef __cplusplus

@@ -1,4 +1,4 @@
-"""Run the precomputed-bases G1 MSM once more after warm-up (for ncu): python tools/msm_run_pre.py LOGN C"""
+"""Run the precomputed-bases G1 MSM once more after warm-up (for ncu): python tools/msm_run_pre.py LOGN C [ROUNDS]"""
 import sys, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
@@ -9,6 +9,8 @@ n = 1 << logn
 sc = cref.random_scalars(n, 300 + logn); ks = cref.random_scalars(n, 400 + logn)
 bases = cref.g1_generator_muls(ks)
 lib.init()
+if len(sys.argv) > 3:
+    lib.msm_set_affine_rounds(int(sys.argv[3]))
 hb = lib.Bases(bases)
 if c:
     hb.precompute(c)
