@@ -147,18 +147,31 @@ __global__ void __launch_bounds__(DG_BA_THREADS, (sizeof(F) > 48 ? 2 : 4))
     }
 
     // ---- phase 1: running product of the denominators ------------------------------------------
+    // The bucket walk and the entry words of output o + 1 are fetched while output o is processed,
+    // so the operand loads of an iteration issue at its top instead of behind two dependent loads.
+    constexpr uint32_t MASK = 0x7fffffffu;
     F run = fone<F>();
-    {
+    if (o0 < o1) {
         uint32_t bo = off_out[b], bo_next = off_out[b + 1], bi = off_in[b], bi_next = off_in[b + 1];
-        for (uint32_t o = o0; o < o1; o++) {
+        uint32_t iN = 0, eN0 = 0, eN1 = 0;
+        bool pairN = false;
+        auto describe = [&](uint32_t o) {
             while (o >= bo_next) {
                 b++;
                 bo = bo_next; bo_next = off_out[b + 1];
                 bi = bi_next; bi_next = off_in[b + 1];
             }
-            uint32_t i0 = bi + 2 * (o - bo);
-            if (i0 + 1 >= bi_next) continue;                             // unpaired last point: copied in phase 3
-            F x1 = ba_load_x<F, GATHER>(in, entries, i0), x2 = ba_load_x<F, GATHER>(in, entries, i0 + 1);
+            iN = bi + 2 * (o - bo);
+            pairN = iN + 1 < bi_next;
+            if (GATHER && pairN) { eN0 = __ldg(&entries[iN]); eN1 = __ldg(&entries[iN + 1]); }
+        };
+        describe(o0);
+        for (uint32_t o = o0; o < o1; o++) {
+            const uint32_t i0 = iN, e0 = eN0, e1 = eN1;
+            const bool pair = pairN;
+            if (o + 1 < o1) describe(o + 1);
+            if (!pair) continue;                                         // unpaired last point: copied in phase 3
+            F x1 = fload<F>(&in[GATHER ? (e0 & MASK) : i0]), x2 = fload<F>(&in[GATHER ? (e1 & MASK) : i0 + 1]);
             F den;
             bool use = true;
             if (__builtin_expect(feq(x1, x2) || fis_zero(x1) || fis_zero(x2), 0)) {
@@ -212,20 +225,37 @@ __global__ void __launch_bounds__(DG_BA_THREADS, (sizeof(F) > 48 ? 2 : 4))
     // ---- phase 3: peel the inverses off backwards and finish the additions -----------------------
     if (o0 < o1) {
         uint32_t bo = off_out[b], bi = off_in[b], bi_next = off_in[b + 1];
-        for (uint32_t o = o1; o-- > o0;) {
+        uint32_t iN = 0, eN0 = 0, eN1 = 0;
+        bool pairN = false;
+        auto describe = [&](uint32_t o) {
             while (o < bo) {
                 b--;
                 bo = off_out[b];
                 bi_next = bi; bi = off_in[b];
             }
-            uint32_t i0 = bi + 2 * (o - bo);
-            Affine<F> p = ba_load_point<F, GATHER>(in, entries, i0);
-            if (i0 + 1 >= bi_next) { aff_store(&out[o], p); continue; }
-            Affine<F> q = ba_load_point<F, GATHER>(in, entries, i0 + 1);
+            iN = bi + 2 * (o - bo);
+            pairN = iN + 1 < bi_next;
+            if (GATHER) {
+                eN0 = __ldg(&entries[iN]);
+                if (pairN) eN1 = __ldg(&entries[iN + 1]);
+            }
+        };
+        describe(o1 - 1);
+        for (uint32_t o = o1; o-- > o0;) {
+            const uint32_t i0 = iN, e0 = eN0, e1 = eN1;
+            const bool pair = pairN;
+            if (o > o0) describe(o - 1);
+            Affine<F> p = aff_load<F>(&in[GATHER ? (e0 & MASK) : i0]);
+            if (GATHER) p.y = fcneg(p.y, (e0 >> 31) != 0);
+            if (!pair) { aff_store(&out[o], p); continue; }
+            Affine<F> q = aff_load<F>(&in[GATHER ? (e1 & MASK) : i0 + 1]);
+            if (GATHER) q.y = fcneg(q.y, (e1 >> 31) != 0);
             F num, den;
             if (__builtin_expect(feq(p.x, q.x) || fis_zero(p.x) || fis_zero(q.x), 0)) {
-                Affine<F> direct;
-                if (!ba_classify_rare(p, q, num, den, direct)) { aff_store(&out[o], direct); continue; }
+                Affine<F> pc = p, qc = q, direct;                        // copies keep p, q out of local memory on the hot path
+                F n2, d2;
+                if (!ba_classify_rare(pc, qc, n2, d2, direct)) { aff_store(&out[o], direct); continue; }
+                num = n2; den = d2;
             } else {
                 num = fsub(q.y, p.y);
                 den = fsub(q.x, p.x);
