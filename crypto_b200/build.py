@@ -7,7 +7,7 @@ from concurrent.futures import ThreadPoolExecutor
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, 'csrc')
 OUT = os.path.join(HERE, 'libdockgpu.so')
-SOURCES = ['capi.cu', 'msm_g1.cu', 'msm_g2.cu', 'batch_g1.cu', 'batch_g2.cu', 'pairing.cu', 'ntt.cu']
+SOURCES = ['capi.cu', 'msm_g1.cu', 'msm_g2.cu', 'batch_g1.cu', 'batch_g2.cu', 'pairing.cu', 'ntt.cu', 'serialize.cu']
 NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-std=c++17', '-O3', '-lineinfo',
               '-Xcompiler', '-fPIC', '-Xcompiler', '-fvisibility=hidden']
 

@@ -31,6 +31,7 @@ EXPORTS = [
     'dg_gt_pow', 'dg_fp12_mul',
     'dg_fold_g1', 'dg_fold_g1_device', 'dg_fold_g2',
     'dg_fr_ntt', 'dg_fr_ntt_device', 'dg_qap_h_from_abc',
+    'dg_g1_serialize', 'dg_g2_serialize', 'dg_g1_deserialize', 'dg_g2_deserialize',
     'dg_prof_enable', 'dg_prof_read_accumulate',
     'dg_dbg_fp_op', 'dg_dbg_fr_op', 'dg_dbg_set_tunable',
 ]
@@ -387,6 +388,36 @@ def qap_h_from_abc(a, b, c, logn):
     o, op = _out(32 << logn)
     _check(lib.dg_qap_h_from_abc(xp, yp, zp, C.c_uint32(logn), op))
     return o[:32 << logn]
+
+
+# ---- ark-serialize wire formats ------------------------------------------------------------------
+def serialize_points(affine, g2=False, compressed=True):
+    """CanonicalSerialize::serialize_compressed / _uncompressed of a vector of affine points -> bytes array."""
+    lib = init()
+    a, ap = _in(affine)
+    aff = G2_AFF if g2 else G1_AFF
+    n = a.size // aff
+    rec = (aff // 2) if compressed else aff
+    o, op = _out(rec * n)
+    fn = lib.dg_g2_serialize if g2 else lib.dg_g1_serialize
+    _check(fn(ap, C.c_size_t(n), C.c_int32(1 if compressed else 0), op))
+    return o[:rec * n]
+
+
+def deserialize_points(data, g2=False, compressed=True, validate=True):
+    """CanonicalDeserialize::deserialize_compressed / _uncompressed (Validate::Yes when validate) of a vector of
+    points -> (affine records, per-element status bytes, number of rejected elements)."""
+    lib = init()
+    a, ap = _in(data)
+    aff = G2_AFF if g2 else G1_AFF
+    rec = (aff // 2) if compressed else aff
+    n = a.size // rec
+    o, op = _out(aff * n)
+    st, stp = _out(n)
+    bad = C.c_size_t(0)
+    fn = lib.dg_g2_deserialize if g2 else lib.dg_g1_deserialize
+    _check(fn(ap, C.c_size_t(n), C.c_int32(1 if compressed else 0), C.c_int32(1 if validate else 0), op, stp, C.byref(bad)))
+    return o[:aff * n], st[:n], int(bad.value)
 
 
 def dbg_fp_op(op_code, a, b):

@@ -180,6 +180,24 @@ int32_t dg_fr_ntt_device(void *data_dev, void *tmp_dev, uint32_t logn, int32_t i
  * coset_fft(ifft c)) / Z(7)), the coefficients the h_query MSM consumes. */
 int32_t dg_qap_h_from_abc(const uint8_t *a, const uint8_t *b, const uint8_t *c, uint32_t logn, uint8_t *out_h);
 
+/* ---- ark-serialize wire formats ("next" row f4 of SURVEY.md 8f) ------------------------------------
+ * CanonicalSerialize::serialize_compressed / serialize_uncompressed and CanonicalDeserialize::
+ * deserialize_compressed / deserialize_uncompressed for vectors of BLS12-381 points, as the reference
+ * reaches them through ArkObjectBytes (utils/src/serde_utils.rs:13-33) and the derives on the proving /
+ * verifying keys (legogroth16/src/data_structures.rs:7-189).  Encoded records are 48 / 96 B (G1
+ * compressed / uncompressed) and 96 / 192 B (G2), big-endian, Zcash flag bits, c1 before c0; the affine
+ * side is the packed Montgomery record of this ABI.  validate != 0 adds the subgroup check of
+ * Validate::Yes.  status (n bytes, may be NULL): 0 ok, 1 malformed (compression flag, coordinate >= p,
+ * stray bits), 2 not on the curve, 3 not in the prime-order subgroup; rejected elements come back as the
+ * identity record and are counted in *invalid_count (may be NULL) -- ark returns Err for the whole
+ * vector when the count is non-zero. */
+int32_t dg_g1_serialize(const uint8_t *affine, size_t n, int32_t compressed, uint8_t *out);
+int32_t dg_g2_serialize(const uint8_t *affine, size_t n, int32_t compressed, uint8_t *out);
+int32_t dg_g1_deserialize(const uint8_t *in, size_t n, int32_t compressed, int32_t validate, uint8_t *out_affine, uint8_t *status,
+                          size_t *invalid_count);
+int32_t dg_g2_deserialize(const uint8_t *in, size_t n, int32_t compressed, int32_t validate, uint8_t *out_affine, uint8_t *status,
+                          size_t *invalid_count);
+
 /* ---- measurement hooks (bench.py) ---------------------------------------------------------------
  * While enabled, every MSM records a CUDA-event pair on its launching stream around the bucket
  * accumulation kernel (the dominant kernel); dg_prof_read_accumulate synchronises the device,

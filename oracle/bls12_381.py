@@ -618,6 +618,184 @@ def g1_compressed(pt):
     return bytes(b)
 
 
+# ------------------------------------------------- ark-serialize wire formats ("next" row f4) ---
+# ark-bls12-381 0.4 (not vendored in /root/reference; Cargo.toml:34) serialises points in the
+# Zcash / IETF format, which the reference reaches through CanonicalSerialize::serialize_compressed /
+# CanonicalDeserialize::deserialize_compressed (utils/src/serde_utils.rs:13-33, the derive on
+# legogroth16/src/data_structures.rs:7-189):  big-endian coordinates; the three top bits of byte 0
+# are flags  0x80 compressed, 0x40 infinity, 0x20 "y is the lexicographically larger root";
+# G2 writes c1 before c0.  Deserialisation with Validate::Yes also checks subgroup membership.
+def fp_sqrt(a):
+    """A square root of a in Fp (p = 3 mod 4) or None."""
+    s = pow(a, (P + 1) // 4, P)
+    return s if (s * s) % P == a % P else None
+
+def fp2_sqrt(a):
+    """A square root of a in Fp2 = Fp[u]/(u^2+1) or None (norm method)."""
+    c0, c1 = a[0] % P, a[1] % P
+    if c1 == 0:
+        s = fp_sqrt(c0)
+        if s is not None:
+            return (s, 0)
+        s = fp_sqrt((-c0) % P)            # (t u)^2 = -t^2
+        return None if s is None else (0, s)
+    n = fp_sqrt((c0 * c0 + c1 * c1) % P)
+    if n is None:
+        return None
+    for nn in (n, (-n) % P):
+        d = ((c0 + nn) * TWO_INV) % P
+        s = fp_sqrt(d)
+        if s is not None and s != 0:
+            r = (s, (c1 * pow(2 * s, P - 2, P)) % P)
+            if fp2_sqr(r) == (c0, c1):
+                return r
+    return None
+
+def fp_lex_largest(y):
+    return y % P > (P - 1) // 2
+
+def fp2_lex_largest(y):
+    return fp_lex_largest(y[1]) if y[1] % P else fp_lex_largest(y[0])
+
+# endomorphisms behind ark-bls12-381's fast subgroup checks (eprint 2021/1130, section 6):
+#   G1:  (beta x, y) == -[x^2] P        G2:  psi(Q) == [x] Q,  psi = twist o Frobenius o untwist
+def _find_beta():
+    g = 2
+    while True:
+        b = pow(g, (P - 1) // 3, P)
+        if b != 1:
+            break
+        g += 1
+    for cand in (b, (b * b) % P):
+        if ((cand * G1_GEN[0]) % P, G1_GEN[1]) == E1.neg(E1.mul(G1_GEN, X_ABS * X_ABS)):
+            return cand
+    raise AssertionError('no cube root of unity matches the G1 endomorphism')
+
+BETA = _find_beta()
+PSI_X = fp2_inv(fp2_pow(XI, (P - 1) // 3))
+PSI_Y = fp2_inv(fp2_pow(XI, (P - 1) // 2))
+
+def g2_psi(q):
+    if q is None:
+        return None
+    return (fp2_mul(fp2_conj(q[0]), PSI_X), fp2_mul(fp2_conj(q[1]), PSI_Y))
+
+assert g2_psi(G2_GEN) == E2.neg(E2.mul(G2_GEN, X_ABS))          # psi acts as [x] on G2, x < 0
+
+def g1_in_subgroup(pt):
+    """Definition: [r] P == O."""
+    return E1.mul(pt, R) is None
+
+def g2_in_subgroup(pt):
+    return E2.mul(pt, R) is None
+
+def g1_in_subgroup_fast(pt):
+    if pt is None:
+        return True
+    return ((BETA * pt[0]) % P, pt[1]) == E1.neg(E1.mul(pt, X_ABS * X_ABS))
+
+def g2_in_subgroup_fast(pt):
+    if pt is None:
+        return True
+    return g2_psi(pt) == E2.neg(E2.mul(pt, X_ABS))
+
+SER_OK, SER_MALFORMED, SER_NOT_ON_CURVE, SER_NOT_IN_SUBGROUP = 0, 1, 2, 3
+
+def g1_serialize(pt, compressed=True):
+    if pt is None:
+        return bytes([0xC0 if compressed else 0x40]) + bytes(47 if compressed else 95)
+    b = bytearray(pt[0].to_bytes(48, 'big'))
+    if compressed:
+        b[0] |= 0x80
+        if fp_lex_largest(pt[1]):
+            b[0] |= 0x20
+        return bytes(b)
+    return bytes(b) + pt[1].to_bytes(48, 'big')
+
+def g2_serialize(pt, compressed=True):
+    if pt is None:
+        return bytes([0xC0 if compressed else 0x40]) + bytes(95 if compressed else 191)
+    b = bytearray(pt[0][1].to_bytes(48, 'big') + pt[0][0].to_bytes(48, 'big'))
+    if compressed:
+        b[0] |= 0x80
+        if fp2_lex_largest(pt[1]):
+            b[0] |= 0x20
+        return bytes(b)
+    return bytes(b) + pt[1][1].to_bytes(48, 'big') + pt[1][0].to_bytes(48, 'big')
+
+def _deser_flags(b0, compressed):
+    return bool(b0 & 0x80) == compressed, bool(b0 & 0x40), bool(b0 & 0x20)
+
+def g1_deserialize(b, compressed=True, validate=True):
+    """-> (status, point).  Malformed = wrong compression flag, coordinate >= p, stray bits with the infinity flag,
+    sort flag on an uncompressed encoding."""
+    ok, inf, largest = _deser_flags(b[0], compressed)
+    body = bytes([b[0] & 0x1F]) + bytes(b[1:])
+    if not ok or (not compressed and largest):
+        return SER_MALFORMED, None
+    if inf:
+        return (SER_OK, None) if not any(body) and not largest else (SER_MALFORMED, None)
+    x = int.from_bytes(body[:48], 'big')
+    if x >= P:
+        return SER_MALFORMED, None
+    if compressed:
+        y = fp_sqrt((x * x * x + 4) % P)
+        if y is None:
+            return SER_NOT_ON_CURVE, None
+        if fp_lex_largest(y) != largest:
+            y = (-y) % P
+    else:
+        y = int.from_bytes(body[48:96], 'big')
+        if y >= P:
+            return SER_MALFORMED, None
+        if not E1.on_curve((x, y)):
+            return SER_NOT_ON_CURVE, None
+    if validate and not g1_in_subgroup((x, y)):
+        return SER_NOT_IN_SUBGROUP, None
+    return SER_OK, (x, y)
+
+def g2_deserialize(b, compressed=True, validate=True):
+    ok, inf, largest = _deser_flags(b[0], compressed)
+    body = bytes([b[0] & 0x1F]) + bytes(b[1:])
+    if not ok or (not compressed and largest):
+        return SER_MALFORMED, None
+    if inf:
+        return (SER_OK, None) if not any(body) and not largest else (SER_MALFORMED, None)
+    x1, x0 = int.from_bytes(body[:48], 'big'), int.from_bytes(body[48:96], 'big')
+    if x0 >= P or x1 >= P:
+        return SER_MALFORMED, None
+    x = (x0, x1)
+    if compressed:
+        y = fp2_sqrt(fp2_add(fp2_mul(fp2_sqr(x), x), (4, 4)))
+        if y is None:
+            return SER_NOT_ON_CURVE, None
+        if fp2_lex_largest(y) != largest:
+            y = fp2_neg(y)
+    else:
+        y1, y0 = int.from_bytes(body[96:144], 'big'), int.from_bytes(body[144:192], 'big')
+        if y0 >= P or y1 >= P:
+            return SER_MALFORMED, None
+        y = (y0, y1)
+        if not E2.on_curve((x, y)):
+            return SER_NOT_ON_CURVE, None
+    if validate and not g2_in_subgroup((x, y)):
+        return SER_NOT_IN_SUBGROUP, None
+    return SER_OK, (x, y)
+
+def curve_point_from_x(curve_is_g2, seed):
+    """A point ON THE CURVE (in general NOT in the prime-order subgroup): first x >= seed-derived start with a root."""
+    rng = SplitMix64(seed)
+    while True:
+        if curve_is_g2:
+            x = (rng.next() * rng.next() * rng.next() % P, rng.next() * rng.next() * rng.next() % P)
+            y = fp2_sqrt(fp2_add(fp2_mul(fp2_sqr(x), x), (4, 4)))
+        else:
+            x = rng.next() * rng.next() * rng.next() * rng.next() % P
+            y = fp_sqrt((x * x * x + 4) % P)
+        if y is not None:
+            return (x, y)
+
+
 # ------------------------------------------------- deterministic inputs ---
 class SplitMix64:
     def __init__(self, seed):

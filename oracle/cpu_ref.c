@@ -639,3 +639,53 @@ EXPORT void ref_qap_h_from_abc(const uint8_t *a_in, const uint8_t *b_in, const u
     free(a); free(b); free(c);
 }
 EXPORT void ref_fr_mul(const uint8_t *a, const uint8_t *b, uint8_t *out) { fr_t x, y, r; memcpy(&x, a, 32); memcpy(&y, b, 32); fr_mul(&r, &x, &y); memcpy(out, &r, 32); }
+
+/* ---- ark-serialize wire format of G1 ("next" row f4; CPU timing baseline and second checker) ----
+ * CanonicalDeserialize::deserialize_compressed for a Vec<G1Affine> with Validate::Yes / ::No
+ * (utils/src/serde_utils.rs:25-33; legogroth16/src/data_structures.rs:150-168): big-endian x with
+ * the Zcash flag bits, y = (x^3 + 4)^((p+1)/4) with the root chosen by the sort flag, subgroup test
+ * (beta x, y) == -[x^2] P as ark-bls12-381 0.4 does it (eprint 2021/1130).
+ * status: 0 ok, 1 malformed, 2 not on the curve, 3 not in the subgroup. */
+EXPORT void ref_g1_deserialize_compressed(const uint8_t *in, size_t n, int validate, uint8_t *out_aff, uint8_t *status) {
+    static const uint64_t X2[4] = {0x0000000100000000ULL, 0xac45a4010001a402ULL, 0, 0};     /* x^2 */
+    fp_t r2, one_raw, beta, b4;
+    memcpy(r2.l, FPC_R2, 48); memcpy(beta.l, FPC_BETA, 48); memcpy(b4.l, FPC_B_G1, 48);
+    fp_set_zero(&one_raw); one_raw.l[0] = 1;
+#pragma omp parallel for schedule(dynamic, 64)
+    for (size_t i = 0; i < n; i++) {
+        const uint8_t *src = in + 48 * i;
+        uint8_t *dst = out_aff + 96 * i;
+        memset(dst, 0, 96);
+        int comp = src[0] & 0x80, inf = src[0] & 0x40, large = (src[0] & 0x20) != 0;
+        if (!comp) { status[i] = 1; continue; }
+        fp_t x;
+        for (int k = 0; k < 6; k++) {
+            uint64_t w = 0;
+            for (int j = 0; j < 8; j++) w = (w << 8) | src[8 * (5 - k) + j];
+            x.l[k] = w;
+        }
+        x.l[5] &= 0x1fffffffffffffffULL;
+        if (inf) { status[i] = (fp_is_zero(&x) && !large) ? 0 : 1; continue; }
+        if (fp_geq_p(x.l)) { status[i] = 1; continue; }
+        g1_aff p; p.inf = 0;
+        fp_mul(&p.x, &x, &r2);
+        fp_t rhs, y, chk, yc;
+        fp_sqr(&rhs, &p.x); fp_mul(&rhs, &rhs, &p.x); fp_add(&rhs, &rhs, &b4);
+        fp_pow(&y, &rhs, FPC_EXP_SQRT, 6);
+        fp_sqr(&chk, &y);
+        if (!fp_eq(&chk, &rhs)) { status[i] = 2; continue; }
+        fp_mul(&yc, &y, &one_raw);                                   /* canonical y */
+        int is_large = 0;
+        for (int k = 5; k >= 0; k--) { if (yc.l[k] != FPC_HALF_P[k]) { is_large = yc.l[k] > FPC_HALF_P[k]; break; } }
+        if (is_large != large) fp_neg(&y, &y);
+        p.y = y;
+        if (validate) {
+            g1_jac q; g1_mul_bigint(&q, &p, X2);
+            g1_aff qa; g1_jac_to_aff(&qa, &q);
+            fp_t bx, ny; fp_mul(&bx, &p.x, &beta); fp_neg(&ny, &p.y);
+            if (qa.inf || !fp_eq(&qa.x, &bx) || !fp_eq(&qa.y, &ny)) { status[i] = 3; continue; }
+        }
+        status[i] = 0;
+        g1_store(dst, &p);
+    }
+}
