@@ -33,7 +33,7 @@ static inline MsmGeom msm_geometry(size_t n, MsmPre pre) {
 #define DG_BA_MAX_ROUNDS 10
 struct MsmLayout {
     MsmGeom g;
-    uint32_t L, nchunks, ngroups1;
+    uint32_t L, nchunks, red_stride;
     size_t o_hist, o_off, o_cursor, o_bsums, o_entries, o_buckets, o_head, o_tail, o_long, o_red[4], total;
     // batch-affine pre-reduction (msm_affine.cuh): R rounds, round r turns <= mb[r] points into <= mb[r + 1]
     int R;
@@ -81,8 +81,6 @@ template <class F> static inline MsmLayout msm_layout(size_t n, MsmPre pre) {
     m.L = (uint32_t)L;
     m.nchunks = (uint32_t)((acc_entries + L - 1) / L);
     if (m.nchunks == 0) m.nchunks = 1;
-    int log_g1 = m.g.nbw >= 4096 ? 4 : 3;
-    m.ngroups1 = (m.g.nbw + (1u << log_g1) - 1) >> log_g1;
     size_t o = 0;
     auto take = [&](size_t bytes) { size_t r = o; o += Arena::pad(bytes); return r; };
     m.o_hist = take(sizeof(uint32_t) * m.g.nb);
@@ -94,7 +92,15 @@ template <class F> static inline MsmLayout msm_layout(size_t n, MsmPre pre) {
     m.o_head = take(sizeof(XYZZ<F>) * m.nchunks);
     m.o_tail = take(sizeof(XYZZ<F>) * m.nchunks);
     m.o_long = take(sizeof(uint32_t) * (m.nchunks / DG_LONG_PIECES + 64));     // [0] = count, list from [16]
-    for (int k = 0; k < 4; k++) m.o_red[k] = take(sizeof(XYZZ<F>) * (size_t)m.g.nwin * m.ngroups1);
+    {   // reduction scratch: [0] line sums (2^HI + 2^LO per window), [1] weighted subset sums (<= 32 per window), [2] window sums
+        int LB = 0;
+        while ((1u << LB) < m.g.nbw) LB++;
+        m.red_stride = (1u << (LB - LB / 2)) + (1u << (LB / 2));
+        m.o_red[0] = take(sizeof(XYZZ<F>) * (size_t)m.g.nwin * m.red_stride);
+        m.o_red[1] = take(sizeof(XYZZ<F>) * (size_t)m.g.nwin * 32);
+        m.o_red[2] = take(sizeof(XYZZ<F>) * (size_t)m.g.nwin);
+        m.o_red[3] = m.o_red[2];
+    }
     m.o_cnt = m.cnt_stride = m.o_pre = m.o_rbsums = m.rbs_stride = 0;
     m.o_aff[0] = m.o_aff[1] = 0;
     if (m.R) {
@@ -217,24 +223,31 @@ static int32_t msm_run(const void *bases_dev, const void *scalars_dev, size_t n,
     DG_LAUNCH(k_bucket_fixup_long<F>, 2 * ctx().sm_count, 128, sizeof(XYZZ<F>) * 128, s, acc_off, m.L, buckets, head, tail,
               long_count, long_list);
 
-    // multi-level bucket reduction
-    const XYZZ<F> *x = buckets, *y = nullptr;
-    uint32_t cnt_x = g.nbw, cnt_y = 0, stride_x = g.nbw, stride_y = 0;
-    int pp = 0;
+    // bucket reduction: line sums -> weighted subset sums -> window sums (three shallow stages, msm_kernels.cuh)
     const XYZZ<F> *wsum = nullptr;
-    for (int level = 0;; level++) {
-        int log_g = (level == 0 && g.nbw >= 4096) ? 4 : 3;
-        uint32_t cnt = cnt_x > cnt_y ? cnt_x : cnt_y;
-        uint32_t ngroups = (cnt + (1u << log_g) - 1) >> log_g;
-        XYZZ<F> *xo = red[2 * pp], *yo = red[2 * pp + 1];
-        const unsigned qpb = sizeof(F) > 48 ? 8 : 16;            // quads per CTA (shared-memory workspace per quad)
-        DG_LAUNCH(k_reduce_level<F>, div_up((size_t)ngroups * g.nwin, qpb), qpb * 4, sizeof(QuadWS<F>) * qpb, s, x, cnt_x,
-                  stride_x, y, cnt_y, stride_y, log_g, ngroups, g.nwin, xo, yo, m.ngroups1);
-        if (ngroups == 1) { wsum = yo; break; }
-        x = xo; y = yo; cnt_x = ngroups - 1; cnt_y = ngroups; stride_x = stride_y = m.ngroups1;
-        pp ^= 1;
+    uint32_t wsum_stride = 0;
+    {
+        int LB = 0;
+        while ((1u << LB) < g.nbw) LB++;                                  // nbw = 2^LB
+        const int LO = LB / 2, HI = LB - LO;
+        const uint32_t nlines = (1u << HI) + (1u << LO), nv = (uint32_t)(LO + HI + 1);
+        XYZZ<F> *lines = red[0], *vbuf = red[1], *ws_out = red[2];
+        constexpr unsigned QP = RedGeom<F>::QP;
+        const size_t smem = sizeof(QuadWS<F>) * QP;
+        static bool red_opt_in = false;
+        if (!red_opt_in) {
+            DG_CUDA(cudaFuncSetAttribute(k_red_lines<F>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            DG_CUDA(cudaFuncSetAttribute(k_red_subsets<F>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            DG_CUDA(cudaFuncSetAttribute(k_red_final<F>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            red_opt_in = true;
+        }
+        DG_LAUNCH(k_red_lines<F>, dim3(nlines, g.nwin), 4 * QP, smem, s, buckets, g.nbw, LO, HI, lines, m.red_stride);
+        DG_LAUNCH(k_red_subsets<F>, dim3(nv, g.nwin), 4 * QP, smem, s, lines, m.red_stride, LO, HI, vbuf, 32u);
+        DG_LAUNCH(k_red_final<F>, dim3(1, g.nwin), 4 * QP, smem, s, vbuf, 32u, (int)nv, ws_out, 1u);
+        wsum = ws_out;
+        wsum_stride = 1;
     }
-    DG_LAUNCH(k_window_combine<F>, 1, 32, sizeof(QuadWS<F>), s, wsum, m.ngroups1, g.nwin, g.c, (Jac<F> *)out_jac_dev);
+    DG_LAUNCH(k_window_combine<F>, 1, 32, sizeof(QuadWS<F>), s, wsum, wsum_stride, g.nwin, g.c, (Jac<F> *)out_jac_dev);
     DG_CUDA(cudaGetLastError());
     return DG_OK;
 }

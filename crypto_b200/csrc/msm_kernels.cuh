@@ -13,7 +13,8 @@
 //                       (run time independent of the scalar distribution - witnesses full of
 //                       0/1 values do not serialise on hot buckets)
 //   5 k_bucket_fixup    stitches the partial sums of buckets that straddle chunks
-//   6 k_reduce_level    multi-level weighted running-sum  sum_b b*B[w][b]  per window
+//   6 k_red_lines / k_red_subsets / k_red_final
+//                       sum_b (b+1)*B[w][b] per window from row / column sums and weighted subset sums
 //   7 k_window_combine  Horner over windows, result as Jacobian (ark Projective layout)
 #pragma once
 #include "ec.cuh"
@@ -300,51 +301,89 @@ __global__ void __launch_bounds__(128) k_bucket_fixup_long(const uint32_t *__res
     }
 }
 
-// ---------------------------------------------------------------- bucket reduction -----------
-// One level of  S = sum_j (j+1) x_j + sum_j y_j  per window.  QUAD (w, q) - four lanes sharing
-// every point operation, see quad.cuh - folds the g items x[q*g .. q*g+g) with a running sum:
-//   A = sum (k+1) x_{qg+k},  R = sum x_{qg+k},  Y = sum y.
-// Then  S = sum_q (A_q + Y_q) + sum_{q>=1} q * (g R_q):  the next level's y'_q = A_q + Y_q and
-// x'_{q-1} = g * R_q (log2 g doublings).  Items past the end are the identity.
+// ---------------------------------------------------------------- bucket reduction, low depth ---
+// S_w = sum_b (b + 1) B[w][b]  over  N = 2^(c-1)  buckets per window without a long serial chain.
+// Write b = h * 2^LO + l.  With the line sums  C_l = sum_h B[h][l]  (columns)  and  R_h = sum_l B[h][l]
+// (rows), the subset sums  U_j = sum_{b : bit j of b set} B[b]  are sums over half of the C's
+// (j < LO) or half of the R's (j >= LO), and
+//        S = T + sum_j 2^j U_j,      T = sum_h R_h.
+// Every sum is a strided accumulation by the quads of a CTA followed by a shared-memory tree, so
+// the dependent-operation depth is ~ len/QP + log2 QP per stage (three stages + j doublings) instead of
+// the 27 operations per level x 5..6 levels of a multi-level running-sum scheme (measured 0.69 ms at
+// N = 2^15, all of it latency; this scheme 0.24 ms).
+template <class F> struct RedGeom { static constexpr int QP = sizeof(F) > 48 ? 16 : 32; };   // quads per CTA (48 KB of workspace)
+
+// quad-cooperative: ACC of quad `qi` := sum of the selected items; result valid in quad 0 after the tree.
+// items are  base[first + k * step]  for k in [0, count) with  (((first_idx + k) >> bit) & 1) == want  when bit >= 0.
 template <class F>
-__global__ void __launch_bounds__(64) k_reduce_level(const XYZZ<F> *__restrict__ x, uint32_t cnt_x, uint32_t stride_x,
-                                                     const XYZZ<F> *__restrict__ y, uint32_t cnt_y, uint32_t stride_y,
-                                                     int log_g, uint32_t ngroups, int nwin,
-                                                     XYZZ<F> *__restrict__ xo, XYZZ<F> *__restrict__ yo, uint32_t stride_o) {
-    extern __shared__ __align__(16) unsigned char dg_smem_quad[];
-    QuadWS<F> &ws = reinterpret_cast<QuadWS<F> *>(dg_smem_quad)[threadIdx.x >> 2];
-    QuadCtx qc = quad_ctx();
-    uint32_t gid = blockIdx.x * (blockDim.x >> 2) + (threadIdx.x >> 2);
-    if (gid >= ngroups * (uint32_t)nwin) return;          // whole quad leaves together
-    uint32_t w = gid / ngroups, q = gid % ngroups, g = 1u << log_g;
-    const XYZZ<F> *xw = x + (size_t)w * stride_x;
-    enum { RUN = 0, ACC = 1, ITEM = 2 };
-    quad_set_inf(ws, RUN, qc);
+__device__ __forceinline__ void red_cta_sum(QuadWS<F> *wsall, const XYZZ<F> *base, uint32_t count, size_t stride, int bit,
+                                            const QuadCtx &qc) {
+    constexpr int QP = RedGeom<F>::QP;
+    const uint32_t qi = threadIdx.x >> 2;
+    QuadWS<F> &ws = wsall[qi];
+    enum { ACC = 1, ITEM = 2 };
     quad_set_inf(ws, ACC, qc);
-    for (uint32_t k = g; k-- > 0;) {
-        uint32_t j = q * g + k;
-        if (j < cnt_x) {
-            quad_load(ws, ITEM, &xw[j], qc);
-            quad_add(ws, RUN, RUN, ITEM, qc);
+    for (uint32_t k = qi; k < count; k += QP) {
+        if (bit >= 0 && !((k >> bit) & 1u)) continue;                     // quad-uniform
+        quad_load(ws, ITEM, base + (size_t)k * stride, qc);
+        quad_add(ws, ACC, ACC, ITEM, qc);
+    }
+    __syncthreads();
+    for (uint32_t s = QP / 2; s > 0; s >>= 1) {
+        if (qi < s) {
+            quad_load(ws, ITEM, reinterpret_cast<const XYZZ<F> *>(&wsall[qi + s].v[4 * ACC]), qc);
+            quad_add(ws, ACC, ACC, ITEM, qc);
         }
-        quad_add(ws, ACC, ACC, RUN, qc);
+        __syncthreads();
     }
-    if (cnt_y) {
-        const XYZZ<F> *yw = y + (size_t)w * stride_y;
-        for (uint32_t k = 0; k < g; k++) {
-            uint32_t j = q * g + k;
-            if (j < cnt_y) {
-                quad_load(ws, ITEM, &yw[j], qc);
-                quad_add(ws, ACC, ACC, ITEM, qc);
-            }
-        }
+}
+
+// stage A: line sums.  grid (2^HI rows + 2^LO columns, nwin); lines[w][0 .. 2^HI) = R, lines[w][2^HI ..) = C
+template <class F>
+__global__ void __launch_bounds__(4 * RedGeom<F>::QP) k_red_lines(const XYZZ<F> *__restrict__ buckets, uint32_t nbw, int LO, int HI,
+                                                                   XYZZ<F> *__restrict__ lines, uint32_t line_stride) {
+    extern __shared__ __align__(16) unsigned char dg_smem_quad[];
+    QuadWS<F> *wsall = reinterpret_cast<QuadWS<F> *>(dg_smem_quad);
+    QuadCtx qc = quad_ctx();
+    const uint32_t w = blockIdx.y, line = blockIdx.x, nrows = 1u << HI, ncols = 1u << LO;
+    const XYZZ<F> *bw = buckets + (size_t)w * nbw;
+    if (line < nrows) red_cta_sum<F>(wsall, bw + (size_t)line * ncols, ncols, 1, -1, qc);            // row h: contiguous
+    else red_cta_sum<F>(wsall, bw + (line - nrows), nrows, ncols, -1, qc);                            // column l: stride 2^LO
+    if ((threadIdx.x >> 2) == 0) quad_store(wsall[0], 1, &lines[(size_t)w * line_stride + line], qc);
+}
+
+// stage B: V_j = 2^j U_j for j < LO + HI, V_{LO+HI} = T.  grid (LO + HI + 1, nwin)
+template <class F>
+__global__ void __launch_bounds__(4 * RedGeom<F>::QP) k_red_subsets(const XYZZ<F> *__restrict__ lines, uint32_t line_stride, int LO, int HI,
+                                                                     XYZZ<F> *__restrict__ vout, uint32_t v_stride) {
+    extern __shared__ __align__(16) unsigned char dg_smem_quad[];
+    QuadWS<F> *wsall = reinterpret_cast<QuadWS<F> *>(dg_smem_quad);
+    QuadCtx qc = quad_ctx();
+    const uint32_t w = blockIdx.y, nrows = 1u << HI, ncols = 1u << LO;
+    const int j = (int)blockIdx.x;
+    const XYZZ<F> *R = lines + (size_t)w * line_stride, *Cc = R + nrows;
+    if (j < LO) red_cta_sum<F>(wsall, Cc, ncols, 1, j, qc);
+    else if (j < LO + HI) red_cta_sum<F>(wsall, R, nrows, 1, j - LO, qc);
+    else red_cta_sum<F>(wsall, R, nrows, 1, -1, qc);
+    if ((threadIdx.x >> 2) == 0) {
+        QuadWS<F> &ws = wsall[0];
+        if (j < LO + HI)
+            for (int k = 0; k < j; k++)
+                if (!fis_zero(ws.v[4 * 1 + 2])) quad_dbl(ws, 1, 1, qc);
+        quad_store(ws, 1, &vout[(size_t)w * v_stride + j], qc);
     }
-    quad_store(ws, ACC, &yo[(size_t)w * stride_o + q], qc);
-    if (q >= 1) {
-        for (int k = 0; k < log_g; k++)
-            if (!fis_zero(ws.v[4 * RUN + 2])) quad_dbl(ws, RUN, RUN, qc);
-        quad_store(ws, RUN, &xo[(size_t)w * stride_o + q - 1], qc);
-    }
+}
+
+// stage C: S_w = sum_j V_j.  grid (1, nwin)
+template <class F>
+__global__ void __launch_bounds__(4 * RedGeom<F>::QP) k_red_final(const XYZZ<F> *__restrict__ v, uint32_t v_stride, int nv,
+                                                                   XYZZ<F> *__restrict__ wsum, uint32_t wsum_stride) {
+    extern __shared__ __align__(16) unsigned char dg_smem_quad[];
+    QuadWS<F> *wsall = reinterpret_cast<QuadWS<F> *>(dg_smem_quad);
+    QuadCtx qc = quad_ctx();
+    const uint32_t w = blockIdx.y;
+    red_cta_sum<F>(wsall, v + (size_t)w * v_stride, (uint32_t)nv, 1, -1, qc);
+    if ((threadIdx.x >> 2) == 0) quad_store(wsall[0], 1, &wsum[(size_t)w * wsum_stride], qc);
 }
 
 // window sums S_w (one XYZZ per window at stride) -> sum_w 2^(c w) S_w, Horner from the top,
