@@ -63,13 +63,17 @@ template <class F> static inline MsmLayout msm_layout(size_t n, MsmPre pre) {
     m.R = msm_affine_rounds(n, m.g);
     m.mb[0] = max_entries;
     for (int r = 0; r < m.R; r++) m.mb[r + 1] = (m.mb[r] + m.g.nb) / 2 + 1;     // sum_b ceil(n_b / 2) <= (M + nb) / 2
-    int waves = ctx().tunable[0].load();
-    if (waves < 1) waves = 1;
-    const size_t ba_threads = (size_t)ctx().sm_count * (sizeof(F) > 48 ? 2 : 4) * DG_BA_THREADS * waves;   // resident waves per round
+    // K outputs per thread: whole resident waves of CTAs (a fractional last wave costs a full one), at most kmax
+    // outputs per thread.  tunable 0 = minimum number of waves, tunable 3 = kmax override.
+    int min_waves = ctx().tunable[0].load();
+    if (min_waves < 1) min_waves = 1;
+    size_t kmax = ctx().tunable[3].load() > 0 ? (size_t)ctx().tunable[3].load() : 128;
+    const size_t ba_threads = (size_t)ctx().sm_count * (sizeof(F) > 48 ? 2 : 4) * DG_BA_THREADS;     // one resident wave
     for (int r = 0; r < m.R; r++) {
-        size_t k = (m.mb[r + 1] + ba_threads - 1) / ba_threads;
+        size_t waves = (m.mb[r + 1] + ba_threads * kmax - 1) / (ba_threads * kmax);
+        if (waves < (size_t)min_waves) waves = min_waves;
+        size_t k = (m.mb[r + 1] + ba_threads * waves - 1) / (ba_threads * waves);
         if (k < 16) k = 16;                     // one inversion per CTA batch of 128 x K additions
-        if (k > 128) k = 128;
         m.K[r] = (uint32_t)k;
         m.ctas[r] = (uint32_t)((m.mb[r + 1] + k * DG_BA_THREADS - 1) / (k * DG_BA_THREADS));
     }

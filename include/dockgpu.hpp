@@ -106,6 +106,8 @@ struct G1 {
     static int32_t mul_many(uint64_t h, const uint8_t *s, size_t m, uint8_t *o) { return dg_fixed_base_mul_many_g1(h, s, m, o); }
     static int32_t batch_mul(const uint8_t *p, const uint8_t *s, size_t m, uint8_t *o) { return dg_batch_mul_g1(p, s, m, o); }
     static int32_t normalize(const uint8_t *j, size_t m, uint8_t *o) { return dg_normalize_batch_g1(j, m, o); }
+    static int32_t serialize(const uint8_t *a, size_t n, int c, uint8_t *o) { return dg_g1_serialize(a, n, c, o); }
+    static int32_t deserialize(const uint8_t *i, size_t n, int c, int v, uint8_t *o, uint8_t *st, size_t *bad) { return dg_g1_deserialize(i, n, c, v, o, st, bad); }
 };
 struct G2 {
     static constexpr bool IS_G2 = true;
@@ -116,6 +118,8 @@ struct G2 {
     static int32_t mul_many(uint64_t h, const uint8_t *s, size_t m, uint8_t *o) { return dg_fixed_base_mul_many_g2(h, s, m, o); }
     static int32_t batch_mul(const uint8_t *p, const uint8_t *s, size_t m, uint8_t *o) { return dg_batch_mul_g2(p, s, m, o); }
     static int32_t normalize(const uint8_t *j, size_t m, uint8_t *o) { return dg_normalize_batch_g2(j, m, o); }
+    static int32_t serialize(const uint8_t *a, size_t n, int c, uint8_t *o) { return dg_g2_serialize(a, n, c, o); }
+    static int32_t deserialize(const uint8_t *i, size_t n, int c, int v, uint8_t *o, uint8_t *st, size_t *bad) { return dg_g2_deserialize(i, n, c, v, o, st, bad); }
 };
 using G1Affine = G1::Affine;
 using G1Projective = G1::Projective;
@@ -140,6 +144,29 @@ template <class G> std::vector<typename G::Projective> mul_bigint_batch(const st
     size_t m = p.size() < s.size() ? p.size() : s.size();
     std::vector<typename G::Projective> out(m);
     if (m) check(G::batch_mul(p[0].b.data(), s[0].bytes(), m, out[0].b.data()));
+    return out;
+}
+
+// ---- ark_serialize::{CanonicalSerialize, CanonicalDeserialize} for vectors of points -------------------------
+// (utils/src/serde_utils.rs:13-33; the body after the u64 length prefix of a Vec<Affine>)
+enum class Compress { Yes, No };
+enum class Validate { Yes, No };
+template <class G> std::vector<uint8_t> serialize_points(const std::vector<typename G::Affine> &v, Compress c = Compress::Yes) {
+    const size_t rec = sizeof(typename G::Affine) / (c == Compress::Yes ? 2 : 1);
+    std::vector<uint8_t> out(rec * v.size());
+    if (!v.empty()) check(G::serialize(v[0].b.data(), v.size(), c == Compress::Yes, out.data()));
+    return out;
+}
+// Err(SerializationError::InvalidData) as std::nullopt: any element malformed, off the curve or (Validate::Yes) outside the subgroup
+template <class G>
+std::optional<std::vector<typename G::Affine>> deserialize_points(const std::vector<uint8_t> &bytes, Compress c = Compress::Yes,
+                                                                  Validate val = Validate::Yes) {
+    const size_t rec = sizeof(typename G::Affine) / (c == Compress::Yes ? 2 : 1);
+    if (bytes.size() % rec) return std::nullopt;
+    std::vector<typename G::Affine> out(bytes.size() / rec);
+    size_t bad = 0;
+    if (!out.empty()) check(G::deserialize(bytes.data(), out.size(), c == Compress::Yes, val == Validate::Yes, out[0].b.data(), nullptr, &bad));
+    if (bad) return std::nullopt;
     return out;
 }
 

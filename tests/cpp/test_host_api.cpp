@@ -147,6 +147,30 @@ static void test_mult_checker() {
 // The ABI is re-entrant from worker threads (rayon in the reference, SURVEY.md 8b "Threading"):
 // every thread gets its own stream and scratch arena.  4 threads issue MSMs of different sizes
 // concurrently; every result must equal the oracle's.
+static void test_wire_formats() {                         // CanonicalSerialize / CanonicalDeserialize round trips
+    std::vector<G1Affine> pts = rand_g1(9);
+    pts.push_back(G1Affine{});                                                   // identity
+    std::vector<G2Affine> pts2 = rand_g2(5);
+    for (auto c : {Compress::Yes, Compress::No}) {
+        auto enc = serialize_points<G1>(pts, c);
+        CHECK(enc.size() == pts.size() * (c == Compress::Yes ? 48 : 96));
+        auto dec = deserialize_points<G1>(enc, c, Validate::Yes);
+        CHECK(dec.has_value() && *dec == pts);
+        enc[1] ^= 0x55;                                                          // corrupt the first x coordinate
+        auto bad = deserialize_points<G1>(enc, c, Validate::Yes);
+        CHECK(!bad.has_value() || !((*bad)[0] == pts[0]));
+        auto enc2 = serialize_points<G2>(pts2, c);
+        auto dec2 = deserialize_points<G2>(enc2, c, Validate::Yes);
+        CHECK(dec2.has_value() && *dec2 == pts2);
+    }
+    // the publicly known compressed generator 97f1d3a7...c6bb
+    Fr one = Fr::one();
+    G1Affine g;
+    ref_g1_generator_muls(one.bytes(), 1, g.b.data());
+    auto genc = serialize_points<G1>({g});
+    CHECK(genc[0] == 0x97 && genc[1] == 0xf1 && genc[46] == 0xc6 && genc[47] == 0xbb);
+}
+
 static void test_concurrent_callers() {
     const size_t sizes[4] = {100, 3000, 257, 20000};
     std::vector<std::vector<G1Affine>> bases(4);
@@ -175,6 +199,7 @@ static void test_concurrent_callers() {
 
 int main() {
     init(0);
+    test_wire_formats();
     test_concurrent_callers();
     test_fr();
     test_window_table_and_msm();

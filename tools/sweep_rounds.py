@@ -18,7 +18,7 @@ if len(sys.argv) > 4:
 if len(sys.argv) > 5:
     lib.dbg_set_tunable(1, int(sys.argv[5]))
 if len(sys.argv) > 6:
-    lib.dbg_set_tunable(2, int(sys.argv[6]))
+    lib.dbg_set_tunable(3, int(sys.argv[6]))
 d_s = torch.from_numpy(sc).cuda(); d_o = torch.zeros(288 if G2 else 144, dtype=torch.uint8, device='cuda')
 ts = torch.cuda.Stream(); torch.cuda.set_stream(ts)
 tot = 0
