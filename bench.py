@@ -11,7 +11,7 @@ all-gathered (NCCL, 144 B per rank) and folded on the GPU under the group law.
 `value`   : terms/s with scalars and bases already resident in HBM (dg_msm_g1_handle_device).
             Bases live behind a handle as in the reference's workloads (proving keys / signature
             parameters are fixed across calls) with the 2^(20k)-multiples table built
-            once at upload (dg_bases_precompute, 16 x the base memory at 2^20).  `value_plain_bases` is the
+            once at upload (dg_bases_precompute, 15 x the base memory at 2^20).  `value_plain_bases` is the
             same MSM through dg_msm_g1_device on the raw 96-byte bases with nothing precomputed.
 `e2e`     : terms/s through the host C-ABI call dg_msm_g1 with the scalars in pinned host memory
             copied every step and the 144-byte result read back every step (same handle);
@@ -280,8 +280,8 @@ def run_ours(args, rank, world, local_rank):
     achieved = alg_bytes / (acc_ms * 1e-3) / 1e9 if acc_ms else None
     ip = load_profile_json('int_peak_r01.json') or {}
     imad_peak = (ip.get('imad_lo') or {}).get('ops_per_s')
-    pre_c = args.precompute_window if args.precompute_window else (20 if n >= (1 << 21) else 16)   # dg_bases_precompute default
-    nwin = (256 + pre_c - 1) // pre_c
+    pre_c = args.precompute_window if args.precompute_window else (20 if n >= (1 << 22) else 17)   # dg_bases_precompute default
+    nwin = (254 + pre_c - 1) // pre_c + (1 if 254 % pre_c == 0 else 0)        # msm_ndigits
     _, rounds = lib.msm_plan(n, precomputed_c=pre_c)
     # The dominant kernel: with batch-affine rounds it is round 0 (k_affine_round<Fp, gather>), which visits every
     # (scalar digit, base) entry once and performs half of them as affine additions; without rounds k_accumulate.

@@ -176,11 +176,11 @@ template <class F> static int32_t normalize_host(const uint8_t *jac, size_t m, u
     return DG_OK;
 }
 
-// dg_bases_precompute: replace the resident bases by the table {2^(c*k) * P_i}, k < ceil(256/c)
+// dg_bases_precompute: replace the resident bases by the table {2^(c*k) * P_i}, k < msm_ndigits(c) = ceil(254/c)
 template <class F> static int32_t bases_precompute(HandleRec &rec, int c, cudaStream_t s) {
     if (rec.window) return fail(DG_ERR_BAD_ARG, "bases_precompute: handle already holds a precomputed table");
     if (c < 8 || c > 24) return fail(DG_ERR_BAD_ARG, "bases_precompute: window must be in [8, 24]");
-    int rows = (256 + c - 1) / c;
+    int rows = msm_ndigits(c);
     size_t n = rec.n;
     if ((uint64_t)n * rows >= (1ull << 31)) return fail(DG_ERR_BAD_ARG, "bases_precompute: table exceeds 2^31 points");
     Affine<F> *table = nullptr;

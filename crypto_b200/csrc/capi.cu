@@ -65,7 +65,7 @@ static int32_t read_err_flag(ThreadState &t, const char *what) {
     DG_CUDA(cudaStreamSynchronize(t.stream));
     if (*t.err_flag_host) {
         cudaMemsetAsync(t.err_flag, 0, 4, t.stream);
-        return fail(DG_ERR_BAD_ARG, std::string(what) + ": scalar is not a canonical integer < 2^255");
+        return fail(DG_ERR_BAD_ARG, std::string(what) + ": scalar is not canonical (>= r)");
     }
     return DG_OK;
 }
@@ -256,7 +256,7 @@ int32_t dg_bases_precompute(uint64_t handle, int32_t c) {
     auto it = ctx().handles.find(handle);
     if (it == ctx().handles.end() || (it->second.kind != HandleRec::BASES_G1 && it->second.kind != HandleRec::BASES_G2))
         return fail(DG_ERR_BAD_ARG, "bases_precompute: bad handle");
-    if (c == 0) c = it->second.n >= (1u << 21) ? 20 : 16;     // measured with the batch-affine stage (tools/sweep_rounds.py)
+    if (c == 0) c = it->second.n >= (1u << 22) ? 20 : 17;     // 13 / 15 rows; measured with the batch-affine stage (tools/sweep_rounds.py)
     DG_CUDA(cudaDeviceSynchronize());
     return it->second.kind == HandleRec::BASES_G2 ? bases_precompute_g2(it->second, c, tls().stream)
                                                   : bases_precompute_g1(it->second, c, tls().stream);

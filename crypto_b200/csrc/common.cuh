@@ -88,6 +88,10 @@ static inline unsigned div_up(size_t a, size_t b) { return (unsigned)((a + b - 1
 // Precomputed-bases descriptor: c = 0 means plain bases; otherwise the table holds ceil(256/c)
 // rows of row_stride affine points, row k = 2^(c*k) * P_i (dg_bases_precompute).
 struct MsmPre { int c; uint32_t row_stride; };
+// Signed radix-2^c digits per scalar.  k_digits first maps a canonical scalar s to min(s, r - s) < 2^254 (negating
+// the point), so ceil(254 / c) digits suffice: the top digit is narrower than c bits and stays <= 2^(c-1) even with
+// the carry -- except when c divides 254, where it is full width and its carry needs one more digit.
+static inline int msm_ndigits(int c) { return (254 + c - 1) / c + (254 % c == 0 ? 1 : 0); }
 size_t msm_scratch_bytes_g1(size_t n, MsmPre pre);
 size_t msm_scratch_bytes_g2(size_t n, MsmPre pre);
 void msm_plan_g1(size_t n, MsmPre pre, int *c, int *rounds);

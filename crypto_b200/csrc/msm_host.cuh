@@ -22,11 +22,12 @@ static inline MsmGeom msm_geometry(size_t n, MsmPre pre) {
     }
     MsmGeom g;
     g.c = c;
-    g.ndig = (256 + c - 1) / c;
+    g.ndig = msm_ndigits(c);
     g.nwin = pre.c ? 1 : g.ndig;
     g.nbw = 1u << (c - 1);
     g.nb = g.nbw * (uint32_t)g.nwin;
     g.row_stride = pre.c ? pre.row_stride : 0;
+    g.fp2 = 0;
     return g;
 }
 
@@ -49,16 +50,18 @@ static inline int msm_affine_rounds(size_t n, const MsmGeom &g) {
     int ov = ctx().msm_rounds_override.load();
     if (ov >= 0) return ov > DG_BA_MAX_ROUNDS ? DG_BA_MAX_ROUNDS : ov;
     // measured (tools/sweep_rounds.py): a round pays while the buckets still hold >= 6 points and it
-    // has >= 2^20 additions to spread over the grid
+    // has >= 2^20 (G1) / 2^18 (G2) additions to spread over the grid
     double entries = (double)n * g.ndig, load = entries / (double)g.nb;     // average points per bucket
     int r = 0;
-    while (r < DG_BA_MAX_ROUNDS && load >= 6.0 && entries * 0.5 >= 1048576.0) { load *= 0.5; entries *= 0.5; r++; }
+    const double min_adds = g.fp2 ? 262144.0 : 1048576.0;              // an Fp2 addition is ~3x the work: smaller rounds still pay
+    while (r < DG_BA_MAX_ROUNDS && load >= 6.0 && entries * 0.5 >= min_adds) { load *= 0.5; entries *= 0.5; r++; }
     return r;
 }
 
 template <class F> static inline MsmLayout msm_layout(size_t n, MsmPre pre) {
     MsmLayout m;
     m.g = msm_geometry(n, pre);
+    m.g.fp2 = sizeof(F) > 48;
     size_t max_entries = n * (size_t)m.g.ndig;
     m.R = msm_affine_rounds(n, m.g);
     m.mb[0] = max_entries;
@@ -140,7 +143,7 @@ static int32_t msm_run(const void *bases_dev, const void *scalars_dev, size_t n,
     if (n >= (1ull << 31)) return fail(DG_ERR_BAD_ARG, "msm: n must be < 2^31");
     if ((uint64_t)n * msm_geometry(n, pre).ndig >= 0xffffffffull)
         return fail(DG_ERR_BAD_ARG, "msm: n * digits must fit 32-bit entry offsets (n up to ~2^27)");
-    if (pre.c && (uint64_t)pre.row_stride * ((256 + pre.c - 1) / pre.c) >= (1ull << 31))
+    if (pre.c && (uint64_t)pre.row_stride * msm_ndigits(pre.c) >= (1ull << 31))
         return fail(DG_ERR_BAD_ARG, "msm: precomputed table too large for 31-bit point indices");
     MsmLayout m = msm_layout<F>(n, pre);
     const MsmGeom g = m.g;

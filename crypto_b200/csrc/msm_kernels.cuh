@@ -24,11 +24,12 @@ namespace dg {
 
 struct MsmGeom {
     int c;            // window bits
-    int ndig;         // signed digits per scalar, ndig * c >= 256 so the top digit never overflows
+    int ndig;         // signed digits per scalar (msm_ndigits): the top digit never overflows
     int nwin;         // bucket sets: ndig, or 1 when the bases carry precomputed 2^(c*k) multiples
     uint32_t nbw;     // buckets per set = 2^(c-1)
     uint32_t nb;      // total buckets = nwin * nbw
     uint32_t row_stride;   // precomputed bases: row k (= 2^(c*k) * P_i) starts at k * row_stride; 0 = plain bases
+    int fp2;               // G2 (host-side heuristics only)
 };
 
 // ---------------------------------------------------------------- digits / counting sort -----
@@ -41,6 +42,41 @@ __global__ void __launch_bounds__(256) k_digits(const uint32_t *__restrict__ sca
     const uint4 *sp = reinterpret_cast<const uint4 *>(scalars) + 2 * (size_t)i;
     uint4 lo = __ldg(sp), hi = __ldg(sp + 1);
     uint32_t s[9] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w, 0};
+    // Halve the range: s > (r - 1) / 2 is replaced by r - s with every digit's sign flipped ([s]P = [r - s](-P)), so
+    // the recoded integer is < 2^254 and ceil(254 / c) digits suffice (15 instead of 16 at c = 17).  A scalar >= r
+    // borrows in r - s: not canonical, flagged.
+    bool flip = false;
+    {
+        constexpr uint32_t RM[8] = {DG_R0, DG_R1, DG_R2, DG_R3, DG_R4, DG_R5, DG_R6, DG_R7};
+        uint32_t t[8], borrow = 0;
+#pragma unroll
+        for (int k = 0; k < 8; k++) {                      // t = r - s
+            uint64_t d = (uint64_t)RM[k] - s[k] - borrow;
+            t[k] = (uint32_t)d;
+            borrow = (uint32_t)(d >> 63);
+        }
+        bool zero = true, t_less = false;                  // t < s  <=>  s > r - s
+#pragma unroll
+        for (int k = 7; k >= 0; k--) {
+            if (zero && t[k] != s[k]) { t_less = t[k] < s[k]; zero = false; }
+        }
+        if (borrow) {
+            if (PASS == 0) atomicOr(err_flag, 1u);         // s > r (s == r gives t = 0 and is caught below as s >= r too)
+            return;
+        }
+        bool t_is_zero = true;
+#pragma unroll
+        for (int k = 0; k < 8; k++) t_is_zero &= t[k] == 0;
+        if (t_is_zero) {                                   // s == r
+            if (PASS == 0) atomicOr(err_flag, 1u);
+            return;
+        }
+        if (t_less) {
+            flip = true;
+#pragma unroll
+            for (int k = 0; k < 8; k++) s[k] = t[k];
+        }
+    }
     const uint32_t mask = (1u << g.c) - 1, half = 1u << (g.c - 1);
     uint32_t carry = 0;
     for (int w = 0; w < g.ndig; w++) {
@@ -63,11 +99,11 @@ __global__ void __launch_bounds__(256) k_digits(const uint32_t *__restrict__ sca
                 atomicAdd(&counters[bucket], 1u);
             } else {
                 uint32_t pos = atomicAdd(&counters[bucket], 1u);
-                entries[pos] = (i + (uint32_t)w * g.row_stride) | (neg ? 0x80000000u : 0u);
+                entries[pos] = (i + (uint32_t)w * g.row_stride) | ((neg != flip) ? 0x80000000u : 0u);
             }
         }
     }
-    if (PASS == 0 && carry) atomicOr(err_flag, 1u);   // scalar >= 2^(nwin*c - 1): not a canonical Fr
+    if (PASS == 0 && carry) atomicOr(err_flag, 1u);   // cannot happen for a canonical scalar (msm_ndigits)
 }
 
 // exclusive scan of `in[0..n)` into `out[0..n]` (out[n] = total); 3 small kernels, 4096 items/block

@@ -17,8 +17,9 @@
  *        Fp12 576 B  c0.c0.c0 || c0.c0.c1 || c0.c1.c0 ... c1.c2.c1 (ark field order)
  *    The point at infinity is the all-zero affine record (x = y = 0 is not on either curve);
  *    Jacobian outputs use z = 0 (x = y = R, i.e. ark's Projective::zero()).
- *  - Scalars are canonical (non-Montgomery) 256-bit little-endian integers < 2^255, i.e. the
- *    BigInt<4> that `Fr::into_bigint()` yields and `msm_bigint` receives.
+ *  - Scalars are canonical (non-Montgomery) 256-bit little-endian integers < r, i.e. the
+ *    BigInt<4> that `Fr::into_bigint()` yields and `msm_bigint` receives; anything >= r is
+ *    rejected with DG_ERR_BAD_ARG.
  *  - Thread safety: calls may be issued concurrently from many host threads (rayon workers);
  *    each call uses a per-thread stream and scratch arena.  dg_init is idempotent.
  *  - *_device variants take device pointers and a cudaStream_t (as void*) and do not
@@ -39,7 +40,7 @@ extern "C" {
 
 typedef enum {
     DG_OK = 0,
-    DG_ERR_BAD_ARG = -1,     /* null pointer, bad handle, scalar >= 2^255 ... */
+    DG_ERR_BAD_ARG = -1,     /* null pointer, bad handle, scalar >= r ... */
     DG_ERR_CUDA = -2,        /* a CUDA runtime call failed (message in dg_last_error) */
     DG_ERR_OOM = -3,         /* device allocation failed */
     DG_ERR_NOT_INIT = -4
@@ -65,9 +66,9 @@ int32_t dg_bases_upload_g1(const uint8_t *affine, size_t n, uint64_t *handle);
 int32_t dg_bases_upload_g2(const uint8_t *affine, size_t n, uint64_t *handle);
 int32_t dg_bases_free(uint64_t handle);
 /* Optional, for bases that are reused across many MSMs: replaces the resident points by the table
- * { 2^(c*k) * P_i : k < ceil(256/c) } (ceil(256/c) x the memory, built once on the device).  MSMs
+ * { 2^(c*k) * P_i : k < ceil(254/c) } (ceil(254/c) x the memory, built once on the device).  MSMs
  * through this handle then fold every digit position into ONE bucket set: no window-combination
- * doublings and ceil(256/c) x fewer buckets to reduce.  c = 0 picks a default (16 below 2^21 points, 20 from there).
+ * doublings and ceil(254/c) x fewer buckets to reduce.  c = 0 picks a default (17 below 2^22 points, 20 from there).
  * Results are identical group elements. */
 int32_t dg_bases_precompute(uint64_t handle, int32_t window_bits);
 

@@ -109,3 +109,32 @@ def test_plan_reports_rounds(dg):
     assert c == 20 and r >= 1
     c, r = dg.msm_plan(1 << 20)
     assert c == 16 and r >= 1
+
+
+@pytest.mark.parametrize('c', [5, 15, 17])
+def test_windows_dividing_255_bits(dg, c):
+    """Windows that divide 255 put a full-width digit on top (r >> (255 - c) is ~0.9 * 2^c, above half): its carry
+    must land in the extra sparse digit; the largest canonical scalars must work, inputs >= 2^255 must be rejected."""
+    n = 700
+    bases, ks = h.g1_bases(n, 61)
+    ss = h.rand_scalars(n, 62).copy()
+    sv = ss.reshape(n, 32)
+    for i, v in enumerate((o.R - 1, o.R - 2, (1 << 254) + 12345, (1 << 254) - 1, o.R >> 1)):
+        sv[i] = np.frombuffer(int(v).to_bytes(32, 'little'), np.uint8)
+    dg.msm_set_window(c)
+    try:
+        assert h.affine_g1(dg.msm(bases, ss)) == h.known_dlog_msm_g1(ks, ss)
+        for bad in ((1 << 255), (1 << 255) - 1):
+            t = ss.copy()
+            t[32 * 9:32 * 10] = np.frombuffer(int(bad).to_bytes(32, 'little'), np.uint8)
+            with pytest.raises(dg.DockGpuError):
+                dg.msm(bases, t)
+        assert h.affine_g1(dg.msm(bases, ss)) == h.known_dlog_msm_g1(ks, ss)       # still usable afterwards
+    finally:
+        dg.msm_set_window(0)
+    hb = dg.Bases(bases)
+    try:
+        hb.precompute(17)
+        assert h.affine_g1(dg.msm(hb, ss)) == h.known_dlog_msm_g1(ks, ss)
+    finally:
+        hb.free()
