@@ -35,7 +35,7 @@ static inline MsmGeom msm_geometry(size_t n, MsmPre pre) {
 struct MsmLayout {
     MsmGeom g;
     uint32_t L, nchunks, red_stride;
-    size_t o_hist, o_off, o_cursor, o_bsums, o_entries, o_buckets, o_head, o_tail, o_long, o_red[4], total;
+    size_t o_hist, o_off, o_cursor, o_bsums, o_entries, o_buckets, o_head, o_tail, o_long, o_longpart, o_red[4], total;
     // batch-affine pre-reduction (msm_affine.cuh): R rounds, round r turns <= mb[r] points into <= mb[r + 1]
     int R;
     uint64_t mb[DG_BA_MAX_ROUNDS + 1];
@@ -99,6 +99,7 @@ template <class F> static inline MsmLayout msm_layout(size_t n, MsmPre pre) {
     m.o_head = take(sizeof(XYZZ<F>) * m.nchunks);
     m.o_tail = take(sizeof(XYZZ<F>) * m.nchunks);
     m.o_long = take(sizeof(uint32_t) * (m.nchunks / DG_LONG_PIECES + 64));     // [0] = count, list from [16]
+    m.o_longpart = take(sizeof(XYZZ<F>) * (size_t)(m.nchunks / DG_LONG_PIECES + 1) * DG_LONG_SPLIT);
     {   // reduction scratch: [0] line sums (2^HI + 2^LO per window), [1] weighted subset sums (<= 32 per window), [2] window sums
         int LB = 0;
         while ((1u << LB) < m.g.nbw) LB++;
@@ -227,8 +228,19 @@ static int32_t msm_run(const void *bases_dev, const void *scalars_dev, size_t n,
     uint32_t *long_count = (uint32_t *)(scratch + m.o_long), *long_list = long_count + 16;
     DG_CUDA(cudaMemsetAsync(long_count, 0, 64, s));
     DG_LAUNCH(k_bucket_fixup<F>, div_up(g.nb, 128), 128, 0, s, acc_off, g.nb, m.L, buckets, head, tail, long_count, long_list);
-    DG_LAUNCH(k_bucket_fixup_long<F>, 2 * ctx().sm_count, 128, sizeof(XYZZ<F>) * 128, s, acc_off, m.L, buckets, head, tail,
-              long_count, long_list);
+    {
+        constexpr unsigned QPL = RedGeom<F>::QP;
+        const size_t smem_l = sizeof(QuadWS<F>) * QPL;
+        static bool long_opt_in = false;
+        if (!long_opt_in) {
+            DG_CUDA(cudaFuncSetAttribute(k_fixup_long_part<F>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_l));
+            DG_CUDA(cudaFuncSetAttribute(k_fixup_long_final<F>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_l));
+            long_opt_in = true;
+        }
+        XYZZ<F> *part = (XYZZ<F> *)(scratch + m.o_longpart);
+        DG_LAUNCH(k_fixup_long_part<F>, 4 * ctx().sm_count, 4 * QPL, smem_l, s, acc_off, m.L, head, tail, long_count, long_list, part);
+        DG_LAUNCH(k_fixup_long_final<F>, ctx().sm_count, 4 * QPL, smem_l, s, acc_off, m.L, buckets, long_count, long_list, part);
+    }
 
     // bucket reduction: line sums -> weighted subset sums -> window sums (three shallow stages, msm_kernels.cuh)
     const XYZZ<F> *wsum = nullptr;

@@ -12,7 +12,8 @@
 //                       fixed-length chunk of the sorted entry list into XYZZ partial sums
 //                       (run time independent of the scalar distribution - witnesses full of
 //                       0/1 values do not serialise on hot buckets)
-//   5 k_bucket_fixup    stitches the partial sums of buckets that straddle chunks
+//   5 k_bucket_fixup    stitches the partial sums of buckets that straddle chunks; hot buckets go to
+//                       k_fixup_long_part / k_fixup_long_final (split over up to 32 CTAs of quads)
 //   6 k_red_lines / k_red_subsets / k_red_final
 //                       sum_b (b+1)*B[w][b] per window from row / column sums and weighted subset sums
 //   7 k_window_combine  Horner over windows, result as Jacobian (ark Projective layout)
@@ -276,7 +277,7 @@ __global__ void __launch_bounds__(DG_ACC_THREADS, (sizeof(F) > 48 ? 2 : 3)) k_ac
 
 // Buckets whose pieces span more than DG_LONG_PIECES chunks (hot buckets: skewed scalars such as
 // the 0/1-heavy witnesses of real circuits, or the sparsely populated top window) are queued for
-// k_bucket_fixup_long instead of being summed by one thread.
+// k_fixup_long_part / k_fixup_long_final instead of being summed by one thread.
 #define DG_LONG_PIECES 24
 template <class F>
 __global__ void __launch_bounds__(128) k_bucket_fixup(const uint32_t *__restrict__ off, uint32_t nb, uint32_t L,
@@ -305,38 +306,6 @@ __global__ void __launch_bounds__(128) k_bucket_fixup(const uint32_t *__restrict
     xyzz_store(&buckets[b], acc);
 }
 
-// One CTA per queued bucket: 128 threads each sum a contiguous slice of the pieces, then a
-// shared-memory tree combines the 128 partial sums.
-template <class F>
-__global__ void __launch_bounds__(128) k_bucket_fixup_long(const uint32_t *__restrict__ off, uint32_t L,
-                                                           XYZZ<F> *__restrict__ buckets, const XYZZ<F> *__restrict__ head,
-                                                           const XYZZ<F> *__restrict__ tail, const uint32_t *__restrict__ long_count,
-                                                           const uint32_t *__restrict__ long_list) {
-    extern __shared__ __align__(16) unsigned char dg_smem_long[];
-    XYZZ<F> *sm = reinterpret_cast<XYZZ<F> *>(dg_smem_long);
-    uint32_t k = threadIdx.x, cnt = *long_count;
-    for (uint32_t i = blockIdx.x; i < cnt; i += gridDim.x) {
-        uint32_t b = long_list[i];
-        uint32_t s = off[b], e = off[b + 1];
-        uint32_t t0 = s / L, t1 = (e - 1) / L, np = t1 - t0 + 1;
-        bool first0 = (s == t0 * L);
-        uint32_t per = (np + 127) / 128, lo = k * per, hi = lo + per < np ? lo + per : np;
-        XYZZ<F> acc = xyzz_inf<F>();
-        for (uint32_t j = lo; j < hi; j++) {
-            const XYZZ<F> *src = (j == 0 && !first0) ? &tail[t0] : &head[t0 + j];
-            acc = xyzz_add(acc, xyzz_load<F>(src));
-        }
-        sm[k] = acc;
-        __syncthreads();
-        for (uint32_t st = 64; st > 0; st >>= 1) {
-            if (k < st) sm[k] = xyzz_add(sm[k], sm[k + st]);
-            __syncthreads();
-        }
-        if (k == 0) xyzz_store(&buckets[b], sm[0]);
-        __syncthreads();
-    }
-}
-
 // ---------------------------------------------------------------- bucket reduction, low depth ---
 // S_w = sum_b (b + 1) B[w][b]  over  N = 2^(c-1)  buckets per window without a long serial chain.
 // Write b = h * 2^LO + l.  With the line sums  C_l = sum_h B[h][l]  (columns)  and  R_h = sum_l B[h][l]
@@ -349,11 +318,10 @@ __global__ void __launch_bounds__(128) k_bucket_fixup_long(const uint32_t *__res
 // N = 2^15, all of it latency; this scheme 0.24 ms).
 template <class F> struct RedGeom { static constexpr int QP = sizeof(F) > 48 ? 16 : 32; };   // quads per CTA (48 KB of workspace)
 
-// quad-cooperative: ACC of quad `qi` := sum of the selected items; result valid in quad 0 after the tree.
-// items are  base[first + k * step]  for k in [0, count) with  (((first_idx + k) >> bit) & 1) == want  when bit >= 0.
-template <class F>
-__device__ __forceinline__ void red_cta_sum(QuadWS<F> *wsall, const XYZZ<F> *base, uint32_t count, size_t stride, int bit,
-                                            const QuadCtx &qc) {
+// quad-cooperative: ACC of quad `qi` := sum of the items item(k), k in [0, count) (skipping k with bit `bit` clear when
+// bit >= 0); the total is valid in quad 0 after the shared-memory tree.
+template <class F, class ItemFn>
+__device__ __forceinline__ void red_cta_sum_fn(QuadWS<F> *wsall, uint32_t count, int bit, ItemFn item, const QuadCtx &qc) {
     constexpr int QP = RedGeom<F>::QP;
     const uint32_t qi = threadIdx.x >> 2;
     QuadWS<F> &ws = wsall[qi];
@@ -361,7 +329,7 @@ __device__ __forceinline__ void red_cta_sum(QuadWS<F> *wsall, const XYZZ<F> *bas
     quad_set_inf(ws, ACC, qc);
     for (uint32_t k = qi; k < count; k += QP) {
         if (bit >= 0 && !((k >> bit) & 1u)) continue;                     // quad-uniform
-        quad_load(ws, ITEM, base + (size_t)k * stride, qc);
+        quad_load(ws, ITEM, item(k), qc);
         quad_add(ws, ACC, ACC, ITEM, qc);
     }
     __syncthreads();
@@ -370,6 +338,64 @@ __device__ __forceinline__ void red_cta_sum(QuadWS<F> *wsall, const XYZZ<F> *bas
             quad_load(ws, ITEM, reinterpret_cast<const XYZZ<F> *>(&wsall[qi + s].v[4 * ACC]), qc);
             quad_add(ws, ACC, ACC, ITEM, qc);
         }
+        __syncthreads();
+    }
+}
+template <class F>
+__device__ __forceinline__ void red_cta_sum(QuadWS<F> *wsall, const XYZZ<F> *base, uint32_t count, size_t stride, int bit,
+                                            const QuadCtx &qc) {
+    red_cta_sum_fn<F>(wsall, count, bit, [=](uint32_t k) { return base + (size_t)k * stride; }, qc);
+}
+
+// Hot buckets queued by k_bucket_fixup (skewed scalars such as the 0/1-heavy witnesses of real circuits, or a sparse top
+// window): the pieces of bucket i are split over S_i = min(32, ceil(pieces / 256)) CTAs, each a strided quad sum + tree
+// (k_fixup_long_part), and a second CTA sums the S_i partials (k_fixup_long_final).  A 13 000-point bucket (10 % ones
+// among 2^18 witnesses) took 0.36 ms when one CTA of 128 threads summed it with thread-level additions.
+#define DG_LONG_SPLIT 32
+template <class F> __device__ __forceinline__ uint32_t long_split(uint32_t np) {
+    uint32_t s = (np + 255) / 256;
+    return s > DG_LONG_SPLIT ? DG_LONG_SPLIT : (s ? s : 1);
+}
+template <class F>
+__global__ void __launch_bounds__(4 * RedGeom<F>::QP) k_fixup_long_part(const uint32_t *__restrict__ off, uint32_t L,
+                                                                         const XYZZ<F> *__restrict__ head, const XYZZ<F> *__restrict__ tail,
+                                                                         const uint32_t *__restrict__ long_count,
+                                                                         const uint32_t *__restrict__ long_list, XYZZ<F> *__restrict__ part) {
+    extern __shared__ __align__(16) unsigned char dg_smem_quad[];
+    QuadWS<F> *wsall = reinterpret_cast<QuadWS<F> *>(dg_smem_quad);
+    QuadCtx qc = quad_ctx();
+    const uint32_t cnt = *long_count;
+    for (uint32_t idx = blockIdx.x; idx < cnt * DG_LONG_SPLIT; idx += gridDim.x) {       // CTA-uniform loop
+        const uint32_t i = idx / DG_LONG_SPLIT, si = idx % DG_LONG_SPLIT;
+        const uint32_t b = long_list[i];
+        const uint32_t s = off[b], e = off[b + 1];
+        const uint32_t t0 = s / L, t1 = (e - 1) / L, np = t1 - t0 + 1;
+        const bool first0 = (s == t0 * L);
+        const uint32_t S = long_split<F>(np);
+        if (si >= S) continue;
+        const uint32_t lo = (uint32_t)(((uint64_t)np * si) / S), hi = (uint32_t)(((uint64_t)np * (si + 1)) / S);
+        red_cta_sum_fn<F>(wsall, hi - lo, -1, [=](uint32_t k) {
+            const uint32_t j = lo + k;
+            return (j == 0 && !first0) ? &tail[t0] : &head[t0 + j];
+        }, qc);
+        if ((threadIdx.x >> 2) == 0) quad_store(wsall[0], 1, &part[(size_t)i * DG_LONG_SPLIT + si], qc);
+        __syncthreads();                                                                  // workspace is reused by the next item
+    }
+}
+template <class F>
+__global__ void __launch_bounds__(4 * RedGeom<F>::QP) k_fixup_long_final(const uint32_t *__restrict__ off, uint32_t L,
+                                                                          XYZZ<F> *__restrict__ buckets, const uint32_t *__restrict__ long_count,
+                                                                          const uint32_t *__restrict__ long_list, const XYZZ<F> *__restrict__ part) {
+    extern __shared__ __align__(16) unsigned char dg_smem_quad[];
+    QuadWS<F> *wsall = reinterpret_cast<QuadWS<F> *>(dg_smem_quad);
+    QuadCtx qc = quad_ctx();
+    const uint32_t cnt = *long_count;
+    for (uint32_t i = blockIdx.x; i < cnt; i += gridDim.x) {
+        const uint32_t b = long_list[i];
+        const uint32_t s = off[b], e = off[b + 1];
+        const uint32_t np = (e - 1) / L - s / L + 1;
+        red_cta_sum<F>(wsall, part + (size_t)i * DG_LONG_SPLIT, long_split<F>(np), 1, -1, qc);
+        if ((threadIdx.x >> 2) == 0) quad_store(wsall[0], 1, &buckets[b], qc);
         __syncthreads();
     }
 }
