@@ -30,7 +30,7 @@ struct Context {
     std::atomic<uint64_t> launches{0};
     std::atomic<int> msm_window_override{0};
     std::atomic<int> msm_rounds_override{-1};   // batch-affine rounds: -1 = automatic
-    std::atomic<int> tunable[8] = {};             // dg_dbg_set_tunable: 0 = batch-affine waves per round (0 -> 1)
+    std::atomic<int> tunable[8] = {};             // dg_dbg_set_tunable: 0 = minimum waves per batch-affine round, 3 = max outputs per thread (0 = defaults)
     // optional per-kernel timing of the dominant kernel (bench.py roofline): event pairs recorded
     // on the launching stream around every k_accumulate launch while enabled
     std::atomic<int> prof_enabled{0};

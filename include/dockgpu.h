@@ -208,7 +208,7 @@ int32_t dg_prof_read_accumulate(double *mean_ms, int32_t *count);
 
 /* ---- test hooks (field arithmetic parity; not part of the reference-facing surface) ---------- */
 int32_t dg_dbg_fp_op(int32_t op, const uint8_t *a, const uint8_t *b, size_t n, uint8_t *out);
-/* internal tuning knobs for sweeps (id 0: resident waves per batch-affine round) */
+/* internal tuning knobs for sweeps (id 0: minimum waves per batch-affine round, id 3: max outputs per thread) */
 int32_t dg_dbg_set_tunable(int32_t id, int32_t value);
 int32_t dg_dbg_fr_op(int32_t op, const uint8_t *a, const uint8_t *b, size_t n, uint8_t *out);
 

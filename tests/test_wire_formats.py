@@ -68,3 +68,23 @@ def test_c_restatement_matches_bigint_oracle(cref):
         exp = [o.g1_deserialize(r, True, validate) for r in recs]
         assert list(st) == [e[0] for e in exp]
         assert bytes(out) == b''.join(o.g1_to_bytes(e[1]) for e in exp)
+
+
+def _wire_gold():
+    import json, os
+    return json.load(open(os.path.join(os.path.dirname(__file__), 'golden', 'wire_vectors.json')))
+
+
+def test_oracle_matches_committed_wire_vectors():
+    g = _wire_gold()
+    assert g['public']['g1_generator_compressed'] == G1_GEN_COMPRESSED and g['public']['g2_generator_compressed'] == G2_GEN_COMPRESSED
+    for name, rec, from_b, ser, deser in (('g1', 96, o.g1_from_bytes, o.g1_serialize, o.g1_deserialize),
+                                          ('g2', 192, o.g2_from_bytes, o.g2_serialize, o.g2_deserialize)):
+        aff = bytes.fromhex(g[name]['affine_montgomery'])
+        pts = [from_b(aff[i:i + rec]) for i in range(0, len(aff), rec)]
+        assert b''.join(ser(p, True) for p in pts).hex() == g[name]['compressed']
+        assert b''.join(ser(p, False) for p in pts).hex() == g[name]['uncompressed']
+        bad = bytes.fromhex(g[name]['rejected_compressed'])
+        recs = [bad[i:i + rec // 2] for i in range(0, len(bad), rec // 2)]
+        assert [deser(r, True, True)[0] for r in recs] == g[name]['rejected_status_validated']
+        assert [deser(r, True, False)[0] for r in recs] == g[name]['rejected_status_unvalidated']

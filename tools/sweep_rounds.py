@@ -1,4 +1,5 @@
-"""G1 (or, with env G2=1, G2) MSM timing over (precompute window, batch-affine rounds): python tools/sweep_rounds.py LOGN c1,c2,.. r1,r2,..
+"""G1 (or, with env G2=1, G2) MSM timing over (precompute window, batch-affine rounds):
+python tools/sweep_rounds.py LOGN c1,c2,.. r1,r2,.. [MIN_WAVES [_ [KMAX]]]   (r = -1: automatic rounds)
 c = 0 means plain bases (window from the heuristic, or `cW` entries like 0:14 to force window 14)."""
 import sys, os, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -15,8 +16,6 @@ bases = cref.g2_generator_muls(ks) if G2 else cref.g1_generator_muls(ks)
 lib.init()
 if len(sys.argv) > 4:
     lib.dbg_set_tunable(0, int(sys.argv[4]))
-if len(sys.argv) > 5:
-    lib.dbg_set_tunable(1, int(sys.argv[5]))
 if len(sys.argv) > 6:
     lib.dbg_set_tunable(3, int(sys.argv[6]))
 d_s = torch.from_numpy(sc).cuda(); d_o = torch.zeros(288 if G2 else 144, dtype=torch.uint8, device='cuda')
