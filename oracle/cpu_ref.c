@@ -689,3 +689,87 @@ EXPORT void ref_g1_deserialize_compressed(const uint8_t *in, size_t n, int valid
         g1_store(dst, &p);
     }
 }
+
+/* G2 counterpart: 96-byte records (x.c1 || x.c0 big-endian), y by the norm-method square root in Fp2,
+ * sort flag = lexicographic order on (c1, c0), subgroup test psi(Q) == [x] Q (eprint 2021/1130). */
+static int fp_sqrt_c(fp_t *r, const fp_t *a) {
+    fp_pow(r, a, FPC_EXP_SQRT, 6);
+    fp_t chk; fp_sqr(&chk, r);
+    return fp_eq(&chk, a);
+}
+static int fp_lex_largest_c(const fp_t *mont) {
+    fp_t one_raw, c; fp_set_zero(&one_raw); one_raw.l[0] = 1;
+    fp_mul(&c, mont, &one_raw);
+    for (int k = 5; k >= 0; k--) if (c.l[k] != FPC_HALF_P[k]) return c.l[k] > FPC_HALF_P[k];
+    return 0;
+}
+static int fp2_sqrt_c(fp2_t *out, const fp2_t *a) {
+    fp_t s, t;
+    if (fp_is_zero(&a->c1)) {
+        if (fp_sqrt_c(&s, &a->c0)) { out->c0 = s; fp_set_zero(&out->c1); return 1; }
+        fp_neg(&t, &a->c0);
+        if (fp_sqrt_c(&s, &t)) { fp_set_zero(&out->c0); out->c1 = s; return 1; }
+        return 0;
+    }
+    fp_t n, n2, two_inv;
+    memcpy(two_inv.l, FPC_TWO_INV, 48);
+    fp_sqr(&n2, &a->c0); fp_sqr(&t, &a->c1); fp_add(&n2, &n2, &t);
+    if (!fp_sqrt_c(&n, &n2)) return 0;
+    for (int k = 0; k < 2; k++) {
+        fp_t d;
+        if (k == 0) fp_add(&d, &a->c0, &n); else fp_sub(&d, &a->c0, &n);
+        fp_mul(&d, &d, &two_inv);
+        if (!fp_sqrt_c(&s, &d) || fp_is_zero(&s)) continue;
+        fp_t s2, inv; fp_add(&s2, &s, &s); fp_inv(&inv, &s2);
+        out->c0 = s; fp_mul(&out->c1, &a->c1, &inv);
+        fp2_t chk; fp2_sqr(&chk, out);
+        if (fp2_eq(&chk, a)) return 1;
+    }
+    return 0;
+}
+EXPORT void ref_g2_deserialize_compressed(const uint8_t *in, size_t n, int validate, uint8_t *out_aff, uint8_t *status) {
+    static const uint64_t XABS[4] = {0xd201000000010000ULL, 0, 0, 0};
+    fp_t r2, b4;
+    memcpy(r2.l, FPC_R2, 48); memcpy(b4.l, FPC_B_G1, 48);
+    fp2_t psix, psiy, b2;
+    memcpy(psix.c0.l, FPC_PSI_X0, 48); memcpy(psix.c1.l, FPC_PSI_X1, 48);
+    memcpy(psiy.c0.l, FPC_PSI_Y0, 48); memcpy(psiy.c1.l, FPC_PSI_Y1, 48);
+    b2.c0 = b4; b2.c1 = b4;
+#pragma omp parallel for schedule(dynamic, 32)
+    for (size_t i = 0; i < n; i++) {
+        const uint8_t *src = in + 96 * i;
+        uint8_t *dst = out_aff + 192 * i;
+        memset(dst, 0, 192);
+        int comp = src[0] & 0x80, inf = src[0] & 0x40, large = (src[0] & 0x20) != 0;
+        if (!comp) { status[i] = 1; continue; }
+        fp_t c[2];                                            /* c[0] = x.c1 (first on the wire), c[1] = x.c0 */
+        for (int h = 0; h < 2; h++)
+            for (int k = 0; k < 6; k++) {
+                uint64_t w = 0;
+                for (int j = 0; j < 8; j++) w = (w << 8) | src[48 * h + 8 * (5 - k) + j];
+                c[h].l[k] = w;
+            }
+        c[0].l[5] &= 0x1fffffffffffffffULL;
+        if (inf) { status[i] = (fp_is_zero(&c[0]) && fp_is_zero(&c[1]) && !large) ? 0 : 1; continue; }
+        if (fp_geq_p(c[0].l) || fp_geq_p(c[1].l)) { status[i] = 1; continue; }
+        g2_aff p; p.inf = 0;
+        fp_mul(&p.x.c1, &c[0], &r2); fp_mul(&p.x.c0, &c[1], &r2);
+        fp2_t rhs, y;
+        fp2_sqr(&rhs, &p.x); fp2_mul(&rhs, &rhs, &p.x); fp2_add(&rhs, &rhs, &b2);
+        if (!fp2_sqrt_c(&y, &rhs)) { status[i] = 2; continue; }
+        int is_large = fp_is_zero(&y.c1) ? fp_lex_largest_c(&y.c0) : fp_lex_largest_c(&y.c1);
+        if (is_large != large) fp2_neg(&y, &y);
+        p.y = y;
+        if (validate) {
+            g2_jac q; g2_mul_bigint(&q, &p, XABS);
+            g2_aff qa; g2_jac_to_aff(&qa, &q);
+            fp2_t px, py, t;
+            fp2_conj(&t, &p.x); fp2_mul(&px, &t, &psix);
+            fp2_conj(&t, &p.y); fp2_mul(&py, &t, &psiy);
+            fp2_neg(&py, &py);                                  /* psi(Q) == -[|x|] Q  <=>  [|x|] Q == (psi_x, -psi_y) */
+            if (qa.inf || !fp2_eq(&qa.x, &px) || !fp2_eq(&qa.y, &py)) { status[i] = 3; continue; }
+        }
+        status[i] = 0;
+        g2_store(dst, &p);
+    }
+}

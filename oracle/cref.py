@@ -90,6 +90,14 @@ def g1_deserialize_compressed(data, validate=True):
     return out, st[:n]
 
 
+def g2_deserialize_compressed(data, validate=True):
+    d, dp = _u8(_as_np(data)); n = d.size // 96
+    out = np.zeros(192 * n, np.uint8); st = np.zeros(max(n, 1), np.uint8)
+    lib().ref_g2_deserialize_compressed(dp, C.c_size_t(n), C.c_int(1 if validate else 0), out.ctypes.data_as(C.c_void_p),
+                                        st.ctypes.data_as(C.c_void_p))
+    return out, st[:n]
+
+
 def batch_mul_g2(points, scalars):
     p, pp = _u8(_as_np(points)); s, sp = _u8(_as_np(scalars)); m = s.size // 32
     out = np.zeros(288 * m, np.uint8)

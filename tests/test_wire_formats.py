@@ -88,3 +88,19 @@ def test_oracle_matches_committed_wire_vectors():
         recs = [bad[i:i + rec // 2] for i in range(0, len(bad), rec // 2)]
         assert [deser(r, True, True)[0] for r in recs] == g[name]['rejected_status_validated']
         assert [deser(r, True, False)[0] for r in recs] == g[name]['rejected_status_unvalidated']
+
+
+def test_c_restatement_g2_matches_bigint_oracle(cref):
+    import numpy as np
+    aff = cref.g2_generator_muls(cref.random_scalars(16, 78))
+    pts = [o.g2_from_bytes(bytes(aff[192 * i:192 * i + 192])) for i in range(16)]
+    pts += [None, o.E2.neg(pts[0])] + [o.curve_point_from_x(True, 20 + s) for s in range(3)]
+    recs = [o.g2_serialize(p) for p in pts]
+    g = _wire_gold()['g2']
+    bad = bytes.fromhex(g['rejected_compressed'])
+    recs += [bad[i:i + 96] for i in range(0, len(bad), 96)]
+    for validate in (True, False):
+        out, st = cref.g2_deserialize_compressed(np.frombuffer(b''.join(recs), np.uint8), validate)
+        exp = [o.g2_deserialize(r, True, validate) for r in recs]
+        assert list(st) == [e[0] for e in exp]
+        assert bytes(out) == b''.join(o.g2_to_bytes(e[1]) for e in exp)

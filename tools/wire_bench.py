@@ -36,7 +36,10 @@ aff2 = cref.g2_generator_muls(cref.random_scalars(m, 92))
 t_ser, enc2 = best(lambda: lib.serialize_points(aff2, g2=True))
 t_de, (out2, st2, bad2) = best(lambda: lib.deserialize_points(enc2, g2=True, validate=True))
 assert bad2 == 0 and np.array_equal(out2, aff2)
-res['g2'] = {'points': m, 'serialize_compressed_gpu_ms': t_ser * 1e3, 'deserialize_compressed_validated_gpu_ms': t_de * 1e3, 'ok': True}
+t0 = time.perf_counter(); cout2, cst2 = cref.g2_deserialize_compressed(enc2, True); t_cpu2 = time.perf_counter() - t0
+assert np.array_equal(cout2, aff2) and not cst2.any()
+res['g2'] = {'points': m, 'serialize_compressed_gpu_ms': t_ser * 1e3, 'deserialize_compressed_validated_gpu_ms': t_de * 1e3,
+             'deserialize_compressed_validated_cpu_ms': t_cpu2 * 1e3, 'ok': True}
 res['note'] = 'gpu_ms = host C-ABI call incl. H2D/D2H; cpu_ms = oracle C restatement (OpenMP over points) on the host cores'
 s = json.dumps(res, indent=1)
 if '--out' in sys.argv:
