@@ -226,11 +226,13 @@ def run_ours(args, rank, world, local_rank):
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
-    plain_ms = timed(False)
-
+    # clocks are sampled from here to the end of the e2e loops (every timed region; ~100 ms steps of nvidia-smi)
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
+        time.sleep(0.3)                      # let nvidia-smi come up before the first timed region
+    plain_ms = timed(False)
+
     lib.prof_enable(True)
     lib.prof_read_accumulate()
     launches0 = lib.launch_count()
@@ -238,7 +240,6 @@ def run_ours(args, rank, world, local_rank):
     launches = lib.launch_count() - launches0
     acc_ms, acc_cnt = lib.prof_read_accumulate()
     lib.prof_enable(False)
-    clocks = sampler.stop() if rank == 0 else None
     value = n * world * args.steps / (total_ms * 1e-3)
     value_plain = n * world * args.steps / (plain_ms * 1e-3)
 
@@ -266,6 +267,7 @@ def run_ours(args, rank, world, local_rank):
 
     e2e_plain = e2e(hb)
     e2e_value = e2e(hb_pre)
+    clocks = sampler.stop() if rank == 0 else None
     hb.free()
     hb_pre.free()
 
