@@ -18,6 +18,8 @@ lib.msm_set_affine_rounds(3)          # small inputs do not reach the batch-affi
 ok &= bytes(cref.normalize_batch_g1(lib.msm(bases, ss))) == bytes(cref.normalize_batch_g1(cref.msm_g1(bases, ss)))
 eq = np.tile(ss[:32], n)              # all-equal scalars: one hot bucket per window, doubling / cancellation paths stay cold
 ok &= bytes(cref.normalize_batch_g1(lib.msm(bases, eq))) == bytes(cref.normalize_batch_g1(cref.msm_g1(bases, eq)))
+lib.msm_set_affine_rounds(0)          # ... and without the rounds the hot bucket spans > 24 chunks: k_fixup_long_part / _final
+ok &= bytes(cref.normalize_batch_g1(lib.msm(bases, eq))) == bytes(cref.normalize_batch_g1(cref.msm_g1(bases, eq)))
 hb = lib.Bases(bases).precompute(10)
 ok &= bytes(cref.normalize_batch_g1(lib.msm(hb, ss))) == bytes(cref.normalize_batch_g1(cref.msm_g1(bases, ss)))
 hb.free()
