@@ -41,3 +41,18 @@ def test_length_mismatch_error():
     with pytest.raises(msm.LengthMismatch) as ei:
         v.msm(bytes(96 * 3), [1, 2])
     assert ei.value.min_len == 2
+
+
+def test_serde_framing_errors_without_gpu():
+    """Length framing is checked before anything reaches the GPU."""
+    import struct
+    import pytest
+    from crypto_b200 import serde
+    with pytest.raises(serde.SerializationError) as ei:
+        serde.deserialize_vec(b'\x01\x02', serde.G1)
+    assert ei.value.kind == 'IoError'
+    with pytest.raises(serde.SerializationError) as ei:
+        serde.deserialize_vec(struct.pack('<Q', 3) + bytes(48 * 2), serde.G1)
+    assert ei.value.kind == 'IoError'
+    assert serde.serialized_size(5, serde.G1) == 8 + 5 * 48 and serde.serialized_size(5, serde.G2, compressed=False) == 8 + 5 * 192
+    assert len(serde.deserialize_vec(struct.pack('<Q', 0), serde.G2)) == 0
