@@ -240,3 +240,26 @@ class RandomizedMultChecker:
         scalars = [it[0] for it in items]
         res = VariableBaseMSM(self.group).msm_unchecked(points, scalars)
         return is_zero(res, self.group)
+
+
+# ---- digit recoding of the MSM kernels (specification mirror; csrc/common.cuh msm_ndigits, csrc/msm_kernels.cuh k_digits) ----
+def msm_ndigits(c):
+    """Signed radix-2^c digits per scalar after the range halving s -> min(s, r - s) < 2^254."""
+    return (254 + c - 1) // c + (1 if 254 % c == 0 else 0)
+
+
+def msm_recode(s, c):
+    """(flip, digits): the signed digits k_digits derives for the canonical scalar s, least significant first, each in
+    [-(2^(c-1) - 1), 2^(c-1)]; sum(d_j 2^(c j)) == (r - s if flip else s).  Raises ValueError for s >= r (DG_ERR_BAD_ARG)."""
+    if not 0 <= s < R_MODULUS:
+        raise ValueError('scalar is not canonical (>= r)')
+    flip = R_MODULUS - s < s
+    v = R_MODULUS - s if flip else s
+    half, digits, carry = 1 << (c - 1), [], 0
+    for j in range(msm_ndigits(c)):
+        d = ((v >> (c * j)) & ((1 << c) - 1)) + carry
+        carry = 1 if d > half else 0
+        digits.append(d - (1 << c) if carry else d)
+    if carry:
+        raise AssertionError('top digit carried out: msm_ndigits(%d) is too small' % c)
+    return flip, digits

@@ -56,3 +56,26 @@ def test_serde_framing_errors_without_gpu():
     assert ei.value.kind == 'IoError'
     assert serde.serialized_size(5, serde.G1) == 8 + 5 * 48 and serde.serialized_size(5, serde.G2, compressed=False) == 8 + 5 * 192
     assert len(serde.deserialize_vec(struct.pack('<Q', 0), serde.G2)) == 0
+
+
+def test_msm_digit_recoding_spec():
+    """The digit count the kernels use (msm_ndigits) is enough for EVERY canonical scalar at every window size, and
+    the recoding reproduces the scalar: sum d_j 2^(c j) == min(s, r - s), with the sign folded into `flip`."""
+    import random
+    from crypto_b200 import msm
+    r = msm.R_MODULUS
+    rng = random.Random(7)
+    edge = [0, 1, 2, (r - 1) // 2 - 1, (r - 1) // 2, (r - 1) // 2 + 1, r - 2, r - 1, (1 << 254) - 1, 1 << 253, (1 << 254) % r]
+    for c in range(2, 25):
+        nd = msm.msm_ndigits(c)
+        assert nd * c >= 254 and (nd - 1) * c <= 254
+        half = 1 << (c - 1)
+        worst = [sum(half << (c * j) for j in range(nd)) % r]            # every raw digit at the carry threshold
+        for s in edge + worst + [rng.randrange(r) for _ in range(200)]:
+            flip, d = msm.msm_recode(s % r, c)
+            assert len(d) == nd and all(-half < x <= half for x in d)
+            assert sum(x << (c * j) for j, x in enumerate(d)) == (r - s % r if flip else s % r)
+            assert (r - s % r if flip else s % r) <= (r - 1) // 2 or s % r == 0
+    import pytest
+    with pytest.raises(ValueError):
+        msm.msm_recode(r, 16)
