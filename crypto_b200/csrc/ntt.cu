@@ -250,6 +250,27 @@ static int32_t ntt_host(uint8_t *data, uint32_t logn, int32_t inverse, int32_t c
 
 using namespace dg;
 
+namespace dg {
+// Sparse constraint-matrix times assignment: out[i] = sum_k coeff[k] * w[col[k]], k in [row_ptr[i], row_ptr[i+1]).
+// The `evaluate_constraint` map at the head of LibsnarkReduction::witness_map_from_matrices
+// (legogroth16/src/r1cs_to_qap.rs:150-186) that produces the a, b, c evaluations dg_qap_h_from_abc consumes; CSR
+// as crypto_b200/r1cs.py lays the matrices of a Circom circuit out.  One thread per row (R1CS rows are short).
+__global__ void __launch_bounds__(128) k_fr_spmv(const uint32_t *__restrict__ row_ptr, const uint32_t *__restrict__ col,
+                                                 const Fr *__restrict__ coeff, uint32_t rows, const Fr *__restrict__ w, uint32_t ncols,
+                                                 Fr *__restrict__ out, uint32_t *__restrict__ err_flag) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= rows) return;
+    Fr acc = fr_zero();
+    for (uint32_t k = row_ptr[i]; k < row_ptr[i + 1]; k++) {
+        uint32_t c = col[k];
+        if (c >= ncols) { atomicOr(err_flag, 2u); continue; }
+        acc = fr_add(acc, fr_mul(fr_load(&coeff[k]), fr_load(&w[c])));
+    }
+    fr_store(&out[i], acc);
+}
+
+}  // namespace dg
+
 extern "C" {
 
 int32_t dg_fr_ntt(uint8_t *data, uint32_t logn, int32_t inverse, int32_t coset) { return ntt_host(data, logn, inverse, coset); }
@@ -275,6 +296,39 @@ int32_t dg_fr_into_bigint(const uint8_t *fr_mont, size_t n, uint8_t *out_canonic
     fr_into_bigint_device(d, d, n, t.stream);
     DG_CUDA(cudaMemcpyAsync(out_canonical, d, 32 * n, cudaMemcpyDeviceToHost, t.stream));
     DG_CUDA(cudaStreamSynchronize(t.stream));
+    return DG_OK;
+}
+
+int32_t dg_fr_spmv(const uint32_t *row_ptr, const uint32_t *col, const uint8_t *coeff_mont, size_t rows, size_t nnz, const uint8_t *w_mont,
+                   size_t ncols, uint8_t *out_mont) {
+    int32_t rc = check_init();
+    if (rc) return rc;
+    if (rows == 0) return DG_OK;
+    if (!row_ptr || !out_mont || (nnz && (!col || !coeff_mont || !w_mont))) return fail(DG_ERR_BAD_ARG, "fr_spmv: null pointer");
+    if (rows >= (1ull << 31) || nnz >= (1ull << 32) || ncols >= (1ull << 32)) return fail(DG_ERR_BAD_ARG, "fr_spmv: dimensions too large");
+    if (row_ptr[0] != 0 || row_ptr[rows] != nnz) return fail(DG_ERR_BAD_ARG, "fr_spmv: row_ptr must start at 0 and end at nnz");
+    for (size_t i = 0; i < rows; i++)
+        if (row_ptr[i] > row_ptr[i + 1]) return fail(DG_ERR_BAD_ARG, "fr_spmv: row_ptr must be non-decreasing");
+    ThreadState &t = tls();
+    rc = t.arena.ensure(Arena::pad(4 * (rows + 1)) + Arena::pad(4 * nnz) + Arena::pad(32 * nnz) + Arena::pad(32 * ncols) + Arena::pad(32 * rows),
+                        t.stream);
+    if (rc) return rc;
+    uint32_t *d_rp = t.arena.alloc<uint32_t>(rows + 1), *d_col = t.arena.alloc<uint32_t>(nnz ? nnz : 1);
+    Fr *d_co = t.arena.alloc<Fr>(nnz ? nnz : 1), *d_w = t.arena.alloc<Fr>(ncols ? ncols : 1), *d_o = t.arena.alloc<Fr>(rows);
+    DG_CUDA(cudaMemcpyAsync(d_rp, row_ptr, 4 * (rows + 1), cudaMemcpyHostToDevice, t.stream));
+    if (nnz) {
+        DG_CUDA(cudaMemcpyAsync(d_col, col, 4 * nnz, cudaMemcpyHostToDevice, t.stream));
+        DG_CUDA(cudaMemcpyAsync(d_co, coeff_mont, 32 * nnz, cudaMemcpyHostToDevice, t.stream));
+        DG_CUDA(cudaMemcpyAsync(d_w, w_mont, 32 * ncols, cudaMemcpyHostToDevice, t.stream));
+    }
+    DG_LAUNCH(k_fr_spmv, div_up(rows, 128), 128, 0, t.stream, d_rp, d_col, d_co, (uint32_t)rows, d_w, (uint32_t)ncols, d_o, t.err_flag);
+    DG_CUDA(cudaMemcpyAsync(out_mont, d_o, 32 * rows, cudaMemcpyDeviceToHost, t.stream));
+    DG_CUDA(cudaMemcpyAsync(t.err_flag_host, t.err_flag, 4, cudaMemcpyDeviceToHost, t.stream));
+    DG_CUDA(cudaStreamSynchronize(t.stream));
+    if (*t.err_flag_host) {
+        cudaMemsetAsync(t.err_flag, 0, 4, t.stream);
+        return fail(DG_ERR_BAD_ARG, "fr_spmv: column index out of range");
+    }
     return DG_OK;
 }
 

@@ -30,7 +30,7 @@ EXPORTS = [
     'dg_multi_miller_loop', 'dg_final_exponentiation', 'dg_multi_pairing', 'dg_multi_pairing_is_one', 'dg_multi_pairing_batch',
     'dg_gt_pow', 'dg_fp12_mul',
     'dg_fold_g1', 'dg_fold_g1_device', 'dg_fold_g2',
-    'dg_fr_ntt', 'dg_fr_ntt_device', 'dg_qap_h_from_abc',
+    'dg_fr_ntt', 'dg_fr_ntt_device', 'dg_qap_h_from_abc', 'dg_fr_spmv',
     'dg_g1_serialize', 'dg_g2_serialize', 'dg_g1_deserialize', 'dg_g2_deserialize',
     'dg_prof_enable', 'dg_prof_read_accumulate',
     'dg_dbg_fp_op', 'dg_dbg_fr_op', 'dg_dbg_set_tunable',
@@ -388,6 +388,20 @@ def qap_h_from_abc(a, b, c, logn):
     o, op = _out(32 << logn)
     _check(lib.dg_qap_h_from_abc(xp, yp, zp, C.c_uint32(logn), op))
     return o[:32 << logn]
+
+
+def fr_spmv(row_ptr, col, coeff_mont, w_mont):
+    """CSR matrix (Fr Montgomery coefficients) times assignment vector (Fr Montgomery) -> rows x 32 B Montgomery."""
+    lib = init()
+    rp = np.ascontiguousarray(row_ptr, dtype=np.uint32)
+    cl = np.ascontiguousarray(col, dtype=np.uint32)
+    co, cop = _in(coeff_mont)
+    w, wp = _in(w_mont)
+    rows, nnz, ncols = rp.size - 1, cl.size, w.size // 32
+    o, op = _out(32 * rows)
+    _check(lib.dg_fr_spmv(C.c_void_p(rp.ctypes.data), C.c_void_p(cl.ctypes.data), cop, C.c_size_t(rows), C.c_size_t(nnz), wp,
+                          C.c_size_t(ncols), op))
+    return o[:32 * rows]
 
 
 # ---- ark-serialize wire formats ------------------------------------------------------------------

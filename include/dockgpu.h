@@ -181,6 +181,12 @@ int32_t dg_fr_ntt_device(void *data_dev, void *tmp_dev, uint32_t logn, int32_t i
  * coset_fft(ifft c)) / Z(7)), the coefficients the h_query MSM consumes. */
 int32_t dg_qap_h_from_abc(const uint8_t *a, const uint8_t *b, const uint8_t *c, uint32_t logn, uint8_t *out_h);
 
+/* Sparse constraint matrix times assignment over Fr (CSR; Montgomery elements in and out): the evaluate_constraint
+ * map in front of the witness-map tail, LibsnarkReduction::witness_map_from_matrices
+ * (legogroth16/src/r1cs_to_qap.rs:150-186).  out[i] = sum_{k in [row_ptr[i], row_ptr[i+1])} coeff[k] * w[col[k]]. */
+int32_t dg_fr_spmv(const uint32_t *row_ptr, const uint32_t *col, const uint8_t *coeff_mont, size_t rows, size_t nnz,
+                   const uint8_t *w_mont, size_t ncols, uint8_t *out_mont);
+
 /* ---- ark-serialize wire formats ("next" row f4 of SURVEY.md 8f) ------------------------------------
  * CanonicalSerialize::serialize_compressed / serialize_uncompressed and CanonicalDeserialize::
  * deserialize_compressed / deserialize_uncompressed for vectors of BLS12-381 points, as the reference

@@ -75,3 +75,40 @@ def test_qap_h_from_abc(dg, cref):
     assert np.array_equal(got, exp)
     hv = [o.fr_from_mont_bytes(bytes(got[32 * i:32 * i + 32])) for i in range(n)]
     assert hv[n - 1] == 0                              # deg(h) <= n - 2
+
+
+def test_fr_spmv_vs_bigint(dg):
+    """dg_fr_spmv (the evaluate_constraint map, r1cs_to_qap.rs:150-186) against Python integers: a random CSR matrix with
+    empty rows and repeated columns, and the A / B / C matrices of a squaring-chain circuit read by crypto_b200/r1cs.py."""
+    import random
+    from oracle import bls12_381 as o
+    from crypto_b200 import r1cs
+    rng = random.Random(99)
+    ncols, rows = 37, 50
+    w = [1] + [rng.randrange(o.R) for _ in range(ncols - 1)]
+    rp, col, co = [0], [], []
+    for i in range(rows):
+        for _ in range(0 if i % 7 == 3 else rng.randrange(1, 6)):
+            col.append(rng.randrange(ncols)); co.append(rng.choice([1, o.R - 1, rng.randrange(o.R)]))
+        rp.append(len(col))
+    mont = lambda xs: np.frombuffer(b''.join(o.fr_to_mont_bytes(x) for x in xs), np.uint8)
+    got = bytes(dg.fr_spmv(rp, col, mont(co), mont(w)))
+    exp = [sum(co[k] * w[col[k]] for k in range(rp[i], rp[i + 1])) % o.R for i in range(rows)]
+    assert got == b''.join(o.fr_to_mont_bytes(x) for x in exp)
+    # a circuit: x_{i+1} = x_i^2, 64 constraints
+    n = 64
+    cons = [([(2 + i, 1)], [(2 + i, 1)], [(3 + i if i + 1 < n else 1, 1)]) for i in range(n)]
+    f = r1cs.R1CSFile.new(r1cs.write_r1cs(1, 0, 1, n + 2, cons))
+    xs = [5]
+    for _ in range(n):
+        xs.append(xs[-1] * xs[-1] % o.R)
+    wit = [1, xs[-1]] + xs[:-1]
+    a, b, c = f.evaluate(wit)
+    for (rpk, colk, valk), expk in zip(f.matrices(), (a, b, c)):
+        coeffs = [int.from_bytes(bytes(v), 'little') for v in valk]
+        gotk = bytes(dg.fr_spmv(rpk, colk, mont(coeffs), mont(wit)))
+        assert gotk == b''.join(o.fr_to_mont_bytes(x) for x in expk)
+    assert all((x * y - z) % o.R == 0 for x, y, z in zip(a, b, c))
+    with pytest.raises(dg.DockGpuError):
+        dg.fr_spmv([0, 1], [ncols + 5], mont([1]), mont(w))                      # column out of range
+    assert bytes(dg.fr_spmv([0, 1], [0], mont([7]), mont(w))) == o.fr_to_mont_bytes(7)          # still usable
