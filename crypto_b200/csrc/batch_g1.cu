@@ -23,6 +23,11 @@ __global__ void __launch_bounds__(128) k_dbg_fp_op(int op, const Fp *a, const Fp
 
 namespace dg {
 int32_t bases_precompute_g1(HandleRec &rec, int c, cudaStream_t s) { return bases_precompute<Fp>(rec, c, s); }
+int32_t fold_ptrs_g1(const PtrList &pl, int k, void *out_jac_dev, cudaStream_t s) {
+    DG_LAUNCH(k_fold_jac_ptrs<Fp>, 1, 32, 0, s, pl, (uint32_t)k, (Jac<Fp> *)out_jac_dev);
+    DG_CUDA(cudaGetLastError());
+    return DG_OK;
+}
 }
 
 extern "C" {

@@ -3,6 +3,11 @@
 using namespace dg;
 namespace dg {
 int32_t bases_precompute_g2(HandleRec &rec, int c, cudaStream_t s) { return bases_precompute<Fp2>(rec, c, s); }
+int32_t fold_ptrs_g2(const PtrList &pl, int k, void *out_jac_dev, cudaStream_t s) {
+    DG_LAUNCH(k_fold_jac_ptrs<Fp2>, 1, 32, 0, s, pl, (uint32_t)k, (Jac<Fp2> *)out_jac_dev);
+    DG_CUDA(cudaGetLastError());
+    return DG_OK;
+}
 }
 extern "C" {
 int32_t dg_fixed_base_table_g2(const uint8_t *p, size_t hint_n, uint64_t *h) { return fixed_table_build<Fp2>(p, hint_n, h); }

@@ -206,4 +206,13 @@ template <class F> __global__ void k_fold_jac(const Jac<F> *in, uint32_t k, Jac<
     jac_store(out, xyzz_to_jac(acc));
 }
 
+// Same fold with one pointer per partial: on a multi-GPU context the pointers are the other devices' result
+// buffers, loaded over NVLink peer access by this one thread ("all-reduce under the group law").
+template <class F> __global__ void k_fold_jac_ptrs(PtrList in, uint32_t k, Jac<F> *out) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    XYZZ<F> acc = xyzz_inf<F>();
+    for (uint32_t i = 0; i < k; i++) acc = xyzz_add(acc, jac_to_xyzz(jac_load<F>(in.p[i])));
+    jac_store(out, xyzz_to_jac(acc));
+}
+
 }  // namespace dg

@@ -5,26 +5,56 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <atomic>
+#include <condition_variable>
+#include <deque>
+#include <functional>
 #include <mutex>
+#include <set>
 #include <string>
+#include <thread>
 #include <unordered_map>
 #include <vector>
 #include "../../include/dockgpu.h"
 
 namespace dg {
 
+#define DG_MAX_DEVICES 16
+
 struct HandleRec {
-    enum Kind { BASES_G1, BASES_G2, TABLE_G1, TABLE_G2 } kind;
+    enum Kind { BASES_G1, BASES_G2, TABLE_G1, TABLE_G2, SHARDED_G1, SHARDED_G2 } kind;
     void *dev = nullptr;
     size_t n = 0;            // bases: point count; tables: total records
     int window = 0, nwin = 0;   // tables: window geometry; bases: precompute window / rows (0 = plain)
+    int slot = 0;            // index into Context::devices of the GPU that owns `dev`
+    // SHARDED_*: one contiguous base range per device of dg_init_devices; shard d covers
+    // [shard_lo[d], shard_lo[d + 1]) and lives behind the ordinary single-device handle shard_handle[d]
+    std::vector<uint64_t> shard_handle;
+    std::vector<size_t> shard_lo;
+};
+
+// One host thread per device of dg_init_devices: it owns that device's stream and scratch arena (its
+// thread-local ThreadState), so a sharded call is N ordinary single-device calls issued concurrently.
+struct Worker {
+    std::thread th;
+    std::mutex mu;
+    std::condition_variable cv;
+    std::deque<std::function<void()>> q;
+    bool stop = false;
+    void *partial = nullptr;          // 288 B device buffer: this device's partial MSM result (read by the fold over peer memory)
 };
 
 struct Context {
     std::mutex mu;
     bool inited = false;
-    int device = 0;
+    int device = 0;                               // devices[0]: the device every single-GPU entry point runs on
+    int ndev = 0;
+    int devices[DG_MAX_DEVICES] = {};
+    bool peer[DG_MAX_DEVICES] = {};               // devices[0] can load from devices[d] directly (NVLink peer access)
+    Worker *workers[DG_MAX_DEVICES] = {};
     int sm_count = 148;
+    std::mutex sharded_mu;                        // one sharded MSM at a time (the per-device partial buffers are shared)
+    std::mutex attr_mu;
+    std::set<std::pair<int, const void *>> attr_done;   // (device, kernel) pairs whose dynamic shared memory limit is raised
     std::unordered_map<uint64_t, HandleRec> handles;
     uint64_t next_handle = 1;
     std::atomic<uint64_t> launches{0};
@@ -40,10 +70,17 @@ Context &ctx();
 
 // Grow-only device scratch; contents are zeroed before release because scalars may be secret
 // material (vb_accumulator/src/positive.rs:349-352 zeroizes them on the CPU side).
+// Asynchronous users (the *_device entry points return without synchronising) call mark(): the next ensure() on a
+// different stream then waits for that event before handing the same memory out, and the grow path waits for it on
+// the host before freeing.
 struct Arena {
     char *base = nullptr;
     size_t cap = 0, used = 0;
+    cudaStream_t last_stream = nullptr;
+    cudaEvent_t last_event = nullptr;
+    bool pending = false;
     int32_t ensure(size_t bytes, cudaStream_t s);
+    int32_t mark(cudaStream_t s);
     void reset() { used = 0; }
     template <class T> T *alloc(size_t count) {
         size_t bytes = (count * sizeof(T) + 255) & ~(size_t)255;
@@ -57,6 +94,7 @@ struct Arena {
 
 struct ThreadState {
     cudaStream_t stream = nullptr;
+    int slot = 0;                     // device slot this thread drives: 0 for callers, d for the worker of devices[d]
     Arena arena;
     std::string err;
     uint32_t *err_flag = nullptr;     // device word the kernels OR error bits into
@@ -67,6 +105,12 @@ ThreadState &tls();
 
 int32_t fail(int32_t code, const std::string &msg);
 int32_t check_init();
+// Raises a kernel's dynamic shared memory limit once per (device, kernel); safe from concurrent callers.
+int32_t func_smem_opt_in(const void *func, size_t bytes);
+template <class K> static inline int32_t smem_opt_in(K kernel, size_t bytes) { return func_smem_opt_in((const void *)kernel, bytes); }
+// Runs fn(slot) on the worker thread of every device slot in [0, nslots) concurrently; returns the first failure
+// (its message becomes the caller's dg_last_error).
+int32_t run_on_devices(int nslots, const std::function<int32_t(int)> &fn);
 
 #define DG_CUDA(call)                                                                              \
     do {                                                                                           \
@@ -102,6 +146,10 @@ int32_t msm_run_g2(const void *bases_dev, const void *scalars_dev, size_t n, voi
                    uint32_t *err_flag, cudaStream_t s, MsmPre pre);
 void ntt_release_plans();                                                                  // ntt.cu
 int32_t fr_into_bigint_device(const void *in, void *out, size_t n, cudaStream_t s);   // ntt.cu
+// Partial results of a sharded MSM, one Jacobian record per device; entries may point into peer memory (NVLink).
+struct PtrList { const void *p[DG_MAX_DEVICES]; };
+int32_t fold_ptrs_g1(const PtrList &pl, int k, void *out_jac_dev, cudaStream_t s);       // batch_g1.cu
+int32_t fold_ptrs_g2(const PtrList &pl, int k, void *out_jac_dev, cudaStream_t s);       // batch_g2.cu
 int32_t bases_precompute_g1(HandleRec &rec, int c, cudaStream_t s);
 int32_t bases_precompute_g2(HandleRec &rec, int c, cudaStream_t s);
 

@@ -137,6 +137,8 @@ template <class F> __global__ void k_set_jac_inf(Jac<F> *out) {
 template <class F>
 static int32_t msm_run(const void *bases_dev, const void *scalars_dev, size_t n, void *out_jac_dev, char *scratch,
                        uint32_t *err_flag, cudaStream_t s, MsmPre pre) {
+    // The flag reports THIS run: a stale bit from an earlier asynchronous call must not fail a valid one.
+    DG_CUDA(cudaMemsetAsync(err_flag, 0, 4, s));
     if (n == 0) {
         DG_LAUNCH(k_set_jac_inf<F>, 1, 32, 0, s, (Jac<F> *)out_jac_dev);
         return DG_OK;
@@ -202,13 +204,10 @@ static int32_t msm_run(const void *bases_dev, const void *scalars_dev, size_t n,
         acc_points = (const Affine<F> *)(scratch + m.o_aff[(m.R - 1) & 1]);
     }
     // stage 4b: XYZZ accumulation of what is left
-    {
-        static bool smem_opt_in = false;                   // the Fp2 staging buffers exceed the 48 KB default
-        if (!smem_opt_in) {
-            DG_CUDA(cudaFuncSetAttribute(k_accumulate<F, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dg_acc_smem_bytes<F>()));
-            DG_CUDA(cudaFuncSetAttribute(k_accumulate<F, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dg_acc_smem_bytes<F>()));
-            smem_opt_in = true;
-        }
+    {                                                      // the Fp2 staging buffers exceed the 48 KB default
+        int32_t rc = smem_opt_in(k_accumulate<F, false>, dg_acc_smem_bytes<F>());
+        if (!rc) rc = smem_opt_in(k_accumulate<F, true>, dg_acc_smem_bytes<F>());
+        if (rc) return rc;
     }
     if (m.R) {
         auto kfn = k_accumulate<F, true>;
@@ -231,12 +230,9 @@ static int32_t msm_run(const void *bases_dev, const void *scalars_dev, size_t n,
     {
         constexpr unsigned QPL = RedGeom<F>::QP;
         const size_t smem_l = sizeof(QuadWS<F>) * QPL;
-        static bool long_opt_in = false;
-        if (!long_opt_in) {
-            DG_CUDA(cudaFuncSetAttribute(k_fixup_long_part<F>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_l));
-            DG_CUDA(cudaFuncSetAttribute(k_fixup_long_final<F>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_l));
-            long_opt_in = true;
-        }
+        int32_t rc = smem_opt_in(k_fixup_long_part<F>, smem_l);
+        if (!rc) rc = smem_opt_in(k_fixup_long_final<F>, smem_l);
+        if (rc) return rc;
         XYZZ<F> *part = (XYZZ<F> *)(scratch + m.o_longpart);
         DG_LAUNCH(k_fixup_long_part<F>, 4 * ctx().sm_count, 4 * QPL, smem_l, s, acc_off, m.L, head, tail, long_count, long_list, part);
         DG_LAUNCH(k_fixup_long_final<F>, ctx().sm_count, 4 * QPL, smem_l, s, acc_off, m.L, buckets, long_count, long_list, part);
@@ -253,13 +249,10 @@ static int32_t msm_run(const void *bases_dev, const void *scalars_dev, size_t n,
         XYZZ<F> *lines = red[0], *vbuf = red[1], *ws_out = red[2];
         constexpr unsigned QP = RedGeom<F>::QP;
         const size_t smem = sizeof(QuadWS<F>) * QP;
-        static bool red_opt_in = false;
-        if (!red_opt_in) {
-            DG_CUDA(cudaFuncSetAttribute(k_red_lines<F>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            DG_CUDA(cudaFuncSetAttribute(k_red_subsets<F>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            DG_CUDA(cudaFuncSetAttribute(k_red_final<F>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            red_opt_in = true;
-        }
+        int32_t rc = smem_opt_in(k_red_lines<F>, smem);
+        if (!rc) rc = smem_opt_in(k_red_subsets<F>, smem);
+        if (!rc) rc = smem_opt_in(k_red_final<F>, smem);
+        if (rc) return rc;
         DG_LAUNCH(k_red_lines<F>, dim3(nlines, g.nwin), 4 * QP, smem, s, buckets, g.nbw, LO, HI, lines, m.red_stride);
         DG_LAUNCH(k_red_subsets<F>, dim3(nv, g.nwin), 4 * QP, smem, s, lines, m.red_stride, LO, HI, vbuf, 32u);
         DG_LAUNCH(k_red_final<F>, dim3(1, g.nwin), 4 * QP, smem, s, vbuf, 32u, (int)nv, ws_out, 1u);

@@ -565,14 +565,11 @@ __global__ void __launch_bounds__(PAIR_THREADS) k_f12_mul_or_pow(const F12 *a, c
 }
 
 static int32_t pairing_smem_opt_in() {
-    static bool done = false;
-    if (done) return DG_OK;
-    DG_CUDA(cudaFuncSetAttribute(k_miller, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PairSmem)));
-    DG_CUDA(cudaFuncSetAttribute(k_f12_reduce8, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PairSmem)));
-    DG_CUDA(cudaFuncSetAttribute(k_f12_finish, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PairSmem)));
-    DG_CUDA(cudaFuncSetAttribute(k_f12_mul_or_pow, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PairSmem)));
-    done = true;
-    return DG_OK;
+    int32_t rc = smem_opt_in(k_miller, sizeof(PairSmem));
+    if (!rc) rc = smem_opt_in(k_f12_reduce8, sizeof(PairSmem));
+    if (!rc) rc = smem_opt_in(k_f12_finish, sizeof(PairSmem));
+    if (!rc) rc = smem_opt_in(k_f12_mul_or_pow, sizeof(PairSmem));
+    return rc;
 }
 
 // mode: 1 = Miller loop only (conjugated), 3 = Miller + final exponentiation

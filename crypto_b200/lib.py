@@ -15,8 +15,10 @@ G1_AFF, G1_JAC, G2_AFF, G2_JAC, FP12, SCALAR = 96, 144, 192, 288, 576, 32
 
 # every symbol include/dockgpu.h declares (checked by tests/test_abi.py without a GPU)
 EXPORTS = [
-    'dg_init', 'dg_shutdown', 'dg_last_error', 'dg_launch_count', 'dg_sync',
+    'dg_init', 'dg_init_devices', 'dg_device_count', 'dg_shutdown', 'dg_last_error', 'dg_launch_count', 'dg_sync', 'dg_stream_status',
     'dg_bases_upload_g1', 'dg_bases_upload_g2', 'dg_bases_free', 'dg_bases_precompute',
+    'dg_bases_upload_g1_sharded', 'dg_bases_upload_g2_sharded',
+    'dg_msm_g1_sharded', 'dg_msm_g2_sharded', 'dg_msm_unchecked_g1_sharded',
     'dg_msm_g1_handle_device', 'dg_msm_g2_handle_device',
     'dg_msm_unchecked_g1', 'dg_msm_unchecked_g2', 'dg_fr_into_bigint',
     'dg_msm_g1', 'dg_msm_g2', 'dg_msm_g1_device', 'dg_msm_g2_device', 'dg_msm_set_window',
@@ -78,6 +80,33 @@ def init(device=-1):
     return lib
 
 
+def init_devices(devices):
+    """One process driving several GPUs (dg_init_devices); devices[0] is the primary device."""
+    global _inited
+    lib = load()
+    devs = (C.c_int32 * len(devices))(*devices)
+    _check(lib.dg_init_devices(devs, C.c_int32(len(devices))))
+    _inited = True
+    return lib
+
+
+def device_count():
+    n = C.c_int32(0)
+    _check(init().dg_device_count(C.byref(n)))
+    return n.value
+
+
+def shutdown():
+    global _inited
+    _check(load().dg_shutdown())
+    _inited = False
+
+
+def stream_status(stream=0):
+    """Synchronises the stream and raises DockGpuError if the last MSM queued by this thread saw a scalar >= r."""
+    _check(init().dg_stream_status(C.c_void_p(stream)))
+
+
 def launch_count():
     return int(load().dg_launch_count())
 
@@ -122,6 +151,38 @@ class Bases:
         if self.handle:
             _check(load().dg_bases_free(C.c_uint64(self.handle)))
             self.handle = 0
+
+
+class ShardedBases(Bases):
+    """Bases split by contiguous ranges over every device of init_devices (dg_bases_upload_*_sharded)."""
+
+    def __init__(self, affine, g2=False):
+        lib = init()
+        a, ap = _in(affine)
+        self.g2 = g2
+        self.n = a.size // (G2_AFF if g2 else G1_AFF)
+        h = C.c_uint64(0)
+        fn = lib.dg_bases_upload_g2_sharded if g2 else lib.dg_bases_upload_g1_sharded
+        _check(fn(ap, C.c_size_t(self.n), C.byref(h)))
+        self.handle = h.value
+
+
+def msm_sharded(bases, scalars, g2=False, n=None):
+    """dg_msm_*_sharded: one call, every device; `bases` is a ShardedBases handle or affine records."""
+    lib = init()
+    s, sp = _in(scalars)
+    ns = s.size // SCALAR
+    fn = lib.dg_msm_g2_sharded if g2 else lib.dg_msm_g1_sharded
+    o, op = _out(G2_JAC if g2 else G1_JAC)
+    if isinstance(bases, ShardedBases):
+        assert bases.g2 == g2
+        k = min(ns, bases.n) if n is None else n
+        _check(fn(C.c_uint64(bases.handle), None, sp, C.c_size_t(k), op))
+    else:
+        b, bp = _in(bases)
+        k = min(ns, b.size // (G2_AFF if g2 else G1_AFF)) if n is None else n
+        _check(fn(C.c_uint64(0), bp if k else None, sp, C.c_size_t(k), op))
+    return o[:G2_JAC if g2 else G1_JAC]
 
 
 def msm_handle_device(bases, scalars_ptr, n, out_ptr, stream=0):

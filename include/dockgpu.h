@@ -47,9 +47,17 @@ typedef enum {
 } dg_status;
 
 /* ---- lifecycle -------------------------------------------------------------------------- */
-/* Select the CUDA device this process drives (one process per GPU) and create the context.
- * device < 0 keeps the current device.  Idempotent. */
+/* Select the CUDA device this process drives and create the context.  device < 0 keeps the current
+ * device.  Idempotent.  Same as dg_init_devices(&device, 1). */
 int32_t dg_init(int32_t device);
+/* One process driving several GPUs, as the reference is one process with rayon threads
+ * (utils/src/macros.rs:68-84; SURVEY.md 8b "dg_init(devs, ndev)").  devices[0] is the primary device: every
+ * single-GPU entry point below runs there and the *_sharded entry points combine their per-device partial
+ * results there (peer access over NVLink is enabled from devices[0] to the others when available).  One
+ * host worker thread per device is started on the first sharded call.  Calling it again with the same list
+ * is a no-op; a different list needs dg_shutdown first. */
+int32_t dg_init_devices(const int32_t *devices, int32_t ndev);
+int32_t dg_device_count(int32_t *ndev);
 int32_t dg_shutdown(void);
 /* Copies the calling thread's last error message (NUL-terminated, truncated to cap). */
 int32_t dg_last_error(char *buf, size_t cap);
@@ -65,6 +73,11 @@ int32_t dg_sync(void);
 int32_t dg_bases_upload_g1(const uint8_t *affine, size_t n, uint64_t *handle);
 int32_t dg_bases_upload_g2(const uint8_t *affine, size_t n, uint64_t *handle);
 int32_t dg_bases_free(uint64_t handle);
+/* Same, split into one contiguous base range per device of dg_init_devices (sizes differ by at most one):
+ * shard d stays resident on devices[d].  The handle is accepted by dg_msm_*_sharded, dg_bases_precompute
+ * (every device builds the table of its own range) and dg_bases_free. */
+int32_t dg_bases_upload_g1_sharded(const uint8_t *affine, size_t n, uint64_t *handle);
+int32_t dg_bases_upload_g2_sharded(const uint8_t *affine, size_t n, uint64_t *handle);
 /* Optional, for bases that are reused across many MSMs: replaces the resident points by the table
  * { 2^(c*k) * P_i : k < ceil(254/c) } (ceil(254/c) x the memory, built once on the device).  MSMs
  * through this handle then fold every digit position into ONE bucket set: no window-combination
@@ -88,11 +101,26 @@ int32_t dg_msm_g2(uint64_t bases_handle, const uint8_t *bases, const uint8_t *sc
  * the MSM -- the form bbs_plus/src/setup.rs:145 and schnorr_pok/src/pok_generalized_pedersen.rs:97 call. */
 int32_t dg_msm_unchecked_g1(uint64_t bases_handle, const uint8_t *bases, const uint8_t *scalars_fr_mont, size_t n, uint8_t *out_jac);
 int32_t dg_msm_unchecked_g2(uint64_t bases_handle, const uint8_t *bases, const uint8_t *scalars_fr_mont, size_t n, uint8_t *out_jac);
+/* The same calls over every device of dg_init_devices from ONE host thread (SURVEY.md 8b "dg_msm_g1_sharded", 8e):
+ * the bases are split by contiguous ranges (resident behind a *_sharded handle, or scattered from `bases` when the
+ * handle is 0), each device's worker thread copies its slice of the scalars over its own PCIe link and runs the full
+ * Pippenger pipeline, and devices[0] folds the per-device partial results with one kernel that reads them out of
+ * the peers' memory over NVLink.  Same result as dg_msm_g1 on the whole input, bit for bit after normalisation.
+ * Sharded calls are serialised against each other; they may run next to single-GPU calls from other threads. */
+int32_t dg_msm_g1_sharded(uint64_t sharded_handle, const uint8_t *bases, const uint8_t *scalars, size_t n, uint8_t *out_jac);
+int32_t dg_msm_g2_sharded(uint64_t sharded_handle, const uint8_t *bases, const uint8_t *scalars, size_t n, uint8_t *out_jac);
+int32_t dg_msm_unchecked_g1_sharded(uint64_t sharded_handle, const uint8_t *bases, const uint8_t *scalars_fr_mont, size_t n, uint8_t *out_jac);
 /* Fr::into_bigint for n elements (Montgomery -> canonical little-endian integers) */
 int32_t dg_fr_into_bigint(const uint8_t *fr_mont, size_t n, uint8_t *out_canonical);
 /* device-pointer variants; out_jac_dev is device memory (144 / 288 B) */
 int32_t dg_msm_g1_device(const void *bases_dev, const void *scalars_dev, size_t n, void *out_jac_dev, void *stream);
 int32_t dg_msm_g2_device(const void *bases_dev, const void *scalars_dev, size_t n, void *out_jac_dev, void *stream);
+/* The device-pointer variants return as soon as the kernels are queued and therefore cannot report a scalar >= r:
+ * such a scalar contributes nothing and raises a device-side flag owned by the calling thread.  dg_stream_status
+ * synchronises `stream` (NULL: the thread's own stream) and returns DG_ERR_BAD_ARG if the most recent MSM this
+ * thread queued saw one, DG_OK otherwise; the flag is cleared at the start of every MSM.  A thread's scratch arena
+ * is shared by its calls: a call on a different stream first waits (on the device) for the previous one. */
+int32_t dg_stream_status(void *stream);
 /* resident (optionally precomputed) bases behind a handle, scalars and output in device memory */
 int32_t dg_msm_g1_handle_device(uint64_t bases_handle, const void *scalars_dev, size_t n, void *out_jac_dev, void *stream);
 int32_t dg_msm_g2_handle_device(uint64_t bases_handle, const void *scalars_dev, size_t n, void *out_jac_dev, void *stream);
