@@ -408,6 +408,34 @@ EXPORT void ref_fixed_base_table_g1(const uint8_t *point, int window, uint8_t *o
     free(table);
 }
 
+/* sum_i a_i * b_i over the integers (no reduction) as a 576-bit little-endian integer: the O(n) side of the
+ * known-discrete-log identity  sum s_i (k_i G) = (sum s_i k_i mod r) G  that tests and bench.py use to check
+ * MSMs far larger than the oracle's own Pippenger could finish in seconds.  a, b: n x 32 B canonical LE. */
+EXPORT void ref_scalar_dot_wide(const uint8_t *a, const uint8_t *b, size_t n, uint8_t out[72]) {
+    uint64_t acc[9] = {0};
+    for (size_t i = 0; i < n; i++) {
+        const uint64_t *x = (const uint64_t *)(a + 32 * i), *y = (const uint64_t *)(b + 32 * i);
+        uint64_t prod[8] = {0};
+        for (int j = 0; j < 4; j++) {
+            unsigned __int128 carry = 0;
+            for (int k = 0; k < 4; k++) {
+                unsigned __int128 t = (unsigned __int128)x[j] * y[k] + prod[j + k] + carry;
+                prod[j + k] = (uint64_t)t;
+                carry = t >> 64;
+            }
+            prod[j + 4] = (uint64_t)carry;
+        }
+        unsigned __int128 c = 0;
+        for (int k = 0; k < 8; k++) {
+            c += (unsigned __int128)acc[k] + prod[k];
+            acc[k] = (uint64_t)c;
+            c >>= 64;
+        }
+        acc[8] += (uint64_t)c;
+    }
+    memcpy(out, acc, 72);
+}
+
 /* k_i * G1 generator for synthetic bases (fixed-base, fast): out affine m x 96 B */
 EXPORT void ref_g1_generator_muls(const uint8_t *scalars, size_t m, uint8_t *out_aff) {
     g1_aff g; memcpy(&g.x, FPC_G1_X, 48); memcpy(&g.y, FPC_G1_Y, 48); g.inf = 0;

@@ -31,6 +31,15 @@ def lib():
     return _LIB
 
 
+def set_threads(n):
+    """OpenMP threads of the CPU legs (torchrun exports OMP_NUM_THREADS=1; bench.py's CPU arm wants every core)."""
+    lib()
+    try:
+        C.CDLL('libgomp.so.1').omp_set_num_threads(C.c_int(int(n)))
+    except OSError:
+        pass
+
+
 def _u8(a):
     a = np.ascontiguousarray(a, dtype=np.uint8)
     return a, a.ctypes.data_as(C.c_void_p)
@@ -181,6 +190,15 @@ def fp12_one():
     out = np.zeros(576, np.uint8)
     lib().ref_fp12_one(out.ctypes.data_as(C.c_void_p))
     return out
+
+
+def scalar_dot_mod_r(a, b):
+    """(sum_i a_i * b_i) mod r for two arrays of n x 32 B canonical scalars -> Python int."""
+    x, xp = _u8(_as_np(a)); y, yp = _u8(_as_np(b))
+    n = min(x.size, y.size) // 32
+    out = np.zeros(72, np.uint8)
+    lib().ref_scalar_dot_wide(xp, yp, C.c_size_t(n), out.ctypes.data_as(C.c_void_p))
+    return int.from_bytes(bytes(out), 'little') % 0x73EDA753299D7D483339D80809A1D80553BDA402FFFE5BFEFFFFFFFF00000001
 
 
 def random_scalars(n, seed):
