@@ -21,7 +21,7 @@ namespace dg {
 #define DG_MAX_DEVICES 16
 
 struct HandleRec {
-    enum Kind { BASES_G1, BASES_G2, TABLE_G1, TABLE_G2, SHARDED_G1, SHARDED_G2 } kind;
+    enum Kind { BASES_G1, BASES_G2, TABLE_G1, TABLE_G2, SHARDED_G1, SHARDED_G2, R1CS } kind;
     void *dev = nullptr;
     size_t n = 0;            // bases: point count; tables: total records
     int window = 0, nwin = 0;   // tables: window geometry; bases: precompute window / rows (0 = plain)
@@ -30,6 +30,7 @@ struct HandleRec {
     // [shard_lo[d], shard_lo[d + 1]) and lives behind the ordinary single-device handle shard_handle[d]
     std::vector<uint64_t> shard_handle;
     std::vector<size_t> shard_lo;
+    std::vector<uint64_t> meta;      // R1CS: layout of the device blob (ntt.cu R1csMeta)
 };
 
 // One host thread per device of dg_init_devices: it owns that device's stream and scratch arena (its

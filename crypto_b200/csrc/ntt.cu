@@ -13,6 +13,7 @@
 // memory for up to 8 (first pass, contiguous) or 6 (later passes, strided tiles of 8 x 32 B
 // contiguous elements) stages: 3 passes over the data at 2^19.  Twiddles, coset powers and 1/n
 // come from per-size tables built once on the device (plan cache).
+#include <cstring>
 #include <map>
 #include "common.cuh"
 #include "fr.cuh"
@@ -346,6 +347,181 @@ int32_t dg_dbg_fr_op(int32_t op, const uint8_t *a, const uint8_t *b, size_t n, u
     DG_LAUNCH(k_dbg_fr_op, div_up(n, 128), 128, 0, t.stream, op, d_a, d_b, (uint32_t)n, d_o);
     DG_CUDA(cudaMemcpyAsync(out, d_o, 32 * n, cudaMemcpyDeviceToHost, t.stream));
     DG_CUDA(cudaStreamSynchronize(t.stream));
+    return DG_OK;
+}
+
+// ---- device-chained LegoGroth16 prover (rows a18 + f1) ------------------------------------------------------------------
+// The constraint matrices are fixed per circuit, like the proving key: they are uploaded once (dg_r1cs_upload) as one
+// device blob of three CSR matrices.  dg_groth16_prove_msms then runs, for one assignment and without leaving the device,
+//   witness_map_from_matrices   (legogroth16/src/r1cs_to_qap.rs:150-210: A w, B w, C w, the instance rows of a, 3 iFFT,
+//                                3 coset FFT, (ab - c) / Z(7), coset iFFT)
+//   into_bigint of h and of the assignment   (prover.rs:281-283, 291-293, 315-317)
+//   msm_bigint(h_query, h)      (prover.rs:286)
+//   every further MSM of the proof over a contiguous range of the assignment   (prover.rs:299, 326, 334, 344, 363)
+// and copies only the 144 / 288-byte results back.
+struct R1csMeta { uint64_t off_rp[3], off_col[3], off_co[3], nnz[3], ncons, ninputs, nvars; };
+
+static int32_t lookup_r1cs(uint64_t handle, HandleRec &out) {
+    std::lock_guard<std::mutex> lk(ctx().mu);
+    auto it = ctx().handles.find(handle);
+    if (it == ctx().handles.end() || it->second.kind != HandleRec::R1CS) return fail(DG_ERR_BAD_ARG, "bad r1cs handle");
+    if (it->second.slot != tls().slot) return fail(DG_ERR_BAD_ARG, "the r1cs handle lives on another device");
+    out = it->second;
+    return DG_OK;
+}
+
+int32_t dg_r1cs_upload(const uint32_t *const row_ptr[3], const uint32_t *const col[3], const uint8_t *const coeff_mont[3], size_t num_constraints,
+                       size_t num_inputs, size_t num_vars, uint64_t *handle) {
+    int32_t rc = check_init();
+    if (rc) return rc;
+    if (!row_ptr || !col || !coeff_mont || !handle) return fail(DG_ERR_BAD_ARG, "r1cs_upload: null pointer");
+    if (num_constraints == 0 || num_constraints >= (1ull << 28) || num_vars >= (1ull << 31) || num_inputs == 0 || num_inputs > num_vars)
+        return fail(DG_ERR_BAD_ARG, "r1cs_upload: bad dimensions");
+    R1csMeta m = {};
+    m.ncons = num_constraints; m.ninputs = num_inputs; m.nvars = num_vars;
+    size_t total = 0;
+    for (int k = 0; k < 3; k++) {
+        if (!row_ptr[k]) return fail(DG_ERR_BAD_ARG, "r1cs_upload: null row_ptr");
+        if (row_ptr[k][0] != 0) return fail(DG_ERR_BAD_ARG, "r1cs_upload: row_ptr must start at 0");
+        for (size_t i = 0; i < num_constraints; i++)
+            if (row_ptr[k][i] > row_ptr[k][i + 1]) return fail(DG_ERR_BAD_ARG, "r1cs_upload: row_ptr must be non-decreasing");
+        m.nnz[k] = row_ptr[k][num_constraints];
+        if (m.nnz[k] && (!col[k] || !coeff_mont[k])) return fail(DG_ERR_BAD_ARG, "r1cs_upload: null col / coeff");
+        for (size_t j = 0; j < m.nnz[k]; j++)
+            if (col[k][j] >= num_vars) return fail(DG_ERR_BAD_ARG, "r1cs_upload: column index out of range");
+        m.off_rp[k] = total; total += Arena::pad(4 * (num_constraints + 1));
+        m.off_col[k] = total; total += Arena::pad(4 * (m.nnz[k] + 1));
+        m.off_co[k] = total; total += Arena::pad(32 * (m.nnz[k] + 1));
+    }
+    char *blob = nullptr;
+    DG_CUDA(cudaMalloc(&blob, total));
+    ThreadState &t = tls();
+    cudaError_t e = cudaSuccess;
+    for (int k = 0; k < 3 && e == cudaSuccess; k++) {
+        e = cudaMemcpyAsync(blob + m.off_rp[k], row_ptr[k], 4 * (num_constraints + 1), cudaMemcpyHostToDevice, t.stream);
+        if (e == cudaSuccess && m.nnz[k]) e = cudaMemcpyAsync(blob + m.off_col[k], col[k], 4 * m.nnz[k], cudaMemcpyHostToDevice, t.stream);
+        if (e == cudaSuccess && m.nnz[k]) e = cudaMemcpyAsync(blob + m.off_co[k], coeff_mont[k], 32 * m.nnz[k], cudaMemcpyHostToDevice, t.stream);
+    }
+    if (e == cudaSuccess) e = cudaStreamSynchronize(t.stream);
+    if (e != cudaSuccess) { cudaFree(blob); return fail(DG_ERR_CUDA, cudaGetErrorString(e)); }
+    std::lock_guard<std::mutex> lk(ctx().mu);
+    uint64_t h = ctx().next_handle++;
+    HandleRec r;
+    r.kind = HandleRec::R1CS;
+    r.dev = blob; r.n = num_constraints; r.slot = t.slot;
+    r.meta.assign((const uint64_t *)&m, (const uint64_t *)&m + sizeof(m) / 8);
+    ctx().handles[h] = r;
+    *handle = h;
+    return DG_OK;
+}
+
+int32_t dg_r1cs_free(uint64_t handle) {
+    void *dev = nullptr;
+    {
+        std::lock_guard<std::mutex> lk(ctx().mu);
+        auto it = ctx().handles.find(handle);
+        if (it == ctx().handles.end() || it->second.kind != HandleRec::R1CS) return fail(DG_ERR_BAD_ARG, "r1cs_free: bad handle");
+        dev = it->second.dev;
+        ctx().handles.erase(it);
+    }
+    cudaDeviceSynchronize();
+    cudaFree(dev);
+    return DG_OK;
+}
+
+int32_t dg_groth16_prove_msms(uint64_t r1cs_handle, const uint8_t *full_assignment_mont, size_t num_vars, uint64_t h_query_handle,
+                              const uint64_t *job_bases, const uint64_t *job_offset, const uint64_t *job_count, size_t njobs,
+                              uint8_t *out_h_acc_jac, uint8_t *out_jobs_jac, uint8_t *out_h_mont) {
+    int32_t rc = check_init();
+    if (rc) return rc;
+    if (!full_assignment_mont || !out_h_acc_jac || (njobs && (!job_bases || !job_offset || !job_count || !out_jobs_jac)))
+        return fail(DG_ERR_BAD_ARG, "groth16_prove_msms: null pointer");
+    if (njobs > 31) return fail(DG_ERR_BAD_ARG, "groth16_prove_msms: at most 31 MSM jobs per call");
+    HandleRec rr;
+    rc = lookup_r1cs(r1cs_handle, rr);
+    if (rc) return rc;
+    R1csMeta m;
+    memcpy(&m, rr.meta.data(), sizeof(m));
+    if (num_vars != m.nvars) return fail(DG_ERR_BAD_ARG, "groth16_prove_msms: assignment length differs from the circuit's variable count");
+    uint32_t logn = 0;
+    while (((size_t)1 << logn) < m.ncons + m.ninputs) logn++;                  // Radix2EvaluationDomain::new(num_constraints + num_inputs)
+    if (logn > 28) return fail(DG_ERR_BAD_ARG, "groth16_prove_msms: domain too large");
+    const size_t D = (size_t)1 << logn;
+    // bases of every MSM (copies of the records: the table lock is not held while kernels are queued)
+    std::vector<HandleRec> jb(njobs + 1);
+    {
+        std::lock_guard<std::mutex> lk(ctx().mu);
+        for (size_t j = 0; j <= njobs; j++) {
+            uint64_t h = j < njobs ? job_bases[j] : h_query_handle;
+            auto it = ctx().handles.find(h);
+            if (it == ctx().handles.end() || (it->second.kind != HandleRec::BASES_G1 && it->second.kind != HandleRec::BASES_G2))
+                return fail(DG_ERR_BAD_ARG, "groth16_prove_msms: bad bases handle");
+            if (it->second.slot != tls().slot) return fail(DG_ERR_BAD_ARG, "groth16_prove_msms: a bases handle lives on another device");
+            jb[j] = it->second;
+        }
+    }
+    if (jb[njobs].kind != HandleRec::BASES_G1) return fail(DG_ERR_BAD_ARG, "groth16_prove_msms: h_query must be G1");
+    const size_t nh = jb[njobs].n < D ? jb[njobs].n : D;                        // msm_bigint truncates to the shorter side
+    size_t msm_scratch = 0;
+    auto pre_of = [](const HandleRec &r) { return r.window ? MsmPre{r.window, (uint32_t)r.n} : MsmPre{0, 0}; };
+    for (size_t j = 0; j <= njobs; j++) {
+        size_t cnt = j < njobs ? job_count[j] : nh;
+        if (j < njobs && (job_offset[j] > num_vars || cnt > num_vars - job_offset[j])) return fail(DG_ERR_BAD_ARG, "groth16_prove_msms: scalar range outside the assignment");
+        if (cnt > jb[j].n) return fail(DG_ERR_BAD_ARG, "groth16_prove_msms: more scalars than bases");
+        size_t b = jb[j].kind == HandleRec::BASES_G2 ? msm_scratch_bytes_g2(cnt, pre_of(jb[j])) : msm_scratch_bytes_g1(cnt, pre_of(jb[j]));
+        if (b > msm_scratch) msm_scratch = b;
+    }
+    ThreadState &t = tls();
+    cudaStream_t s = t.stream;
+    size_t need = 2 * Arena::pad(32 * num_vars) + 4 * Arena::pad(32 * D) + Arena::pad(288 * (njobs + 1)) + Arena::pad(msm_scratch);
+    rc = t.arena.ensure(need, s);
+    if (rc) return rc;
+    Fr *d_w = t.arena.alloc<Fr>(num_vars), *d_wbig = t.arena.alloc<Fr>(num_vars);
+    Fr *d[3], *tmp;
+    for (int k = 0; k < 3; k++) d[k] = t.arena.alloc<Fr>(D);
+    tmp = t.arena.alloc<Fr>(D);
+    uint8_t *d_res = t.arena.alloc<uint8_t>(288 * (njobs + 1));
+    char *scratch = t.arena.alloc<char>(msm_scratch);
+    DG_CUDA(cudaMemcpyAsync(d_w, full_assignment_mont, 32 * num_vars, cudaMemcpyHostToDevice, s));
+    // a, b, c over the domain: constraint rows, then (a only) the instance variables, zero padding
+    const char *blob = (const char *)rr.dev;
+    for (int k = 0; k < 3; k++) {
+        DG_CUDA(cudaMemsetAsync(d[k] + m.ncons, 0, 32 * (D - m.ncons), s));
+        DG_LAUNCH(k_fr_spmv, div_up(m.ncons, 128), 128, 0, s, (const uint32_t *)(blob + m.off_rp[k]), (const uint32_t *)(blob + m.off_col[k]),
+                  (const Fr *)(blob + m.off_co[k]), (uint32_t)m.ncons, d_w, (uint32_t)num_vars, d[k], t.err_flag);
+    }
+    DG_CUDA(cudaMemcpyAsync(d[0] + m.ncons, d_w, 32 * m.ninputs, cudaMemcpyDeviceToDevice, s));
+    for (int k = 0; k < 3; k++) {
+        rc = ntt_device(d[k], tmp, logn, true, false, s);
+        if (!rc) rc = ntt_device(d[k], tmp, logn, false, true, s);
+        if (rc) return rc;
+    }
+    NttPlan p;
+    rc = get_plan(logn, s, p);
+    if (rc) return rc;
+    DG_LAUNCH(k_qap_pointwise, div_up(D, 256), 256, 0, s, d[0], d[1], d[2], (uint32_t)D, p.consts + 5);
+    rc = ntt_device(d[0], tmp, logn, true, true, s);                            // d[0] = h (Montgomery)
+    if (rc) return rc;
+    if (out_h_mont) DG_CUDA(cudaMemcpyAsync(out_h_mont, d[0], 32 * D, cudaMemcpyDeviceToHost, s));
+    fr_into_bigint_device(d[0], d[1], nh, s);                                   // h_assignment
+    fr_into_bigint_device(d_w, d_wbig, num_vars, s);                            // aux / input assignment
+    uint32_t bad = 0;
+    for (size_t j = 0; j <= njobs; j++) {
+        const bool g2 = jb[j].kind == HandleRec::BASES_G2;
+        const size_t cnt = j < njobs ? job_count[j] : nh;
+        const void *sc = j < njobs ? (const void *)(d_wbig + job_offset[j]) : (const void *)d[1];
+        rc = g2 ? msm_run_g2(jb[j].dev, sc, cnt, d_res + 288 * j, scratch, t.err_flag, s, pre_of(jb[j]))
+                : msm_run_g1(jb[j].dev, sc, cnt, d_res + 288 * j, scratch, t.err_flag, s, pre_of(jb[j]));
+        if (rc) return rc;
+        // msm_run clears the flag when it starts: collect it per MSM
+        DG_CUDA(cudaMemcpyAsync(t.err_flag_host + 1 + (j & 31), t.err_flag, 4, cudaMemcpyDeviceToHost, s));
+    }
+    for (size_t j = 0; j < njobs; j++)
+        DG_CUDA(cudaMemcpyAsync(out_jobs_jac + 288 * j, d_res + 288 * j, jb[j].kind == HandleRec::BASES_G2 ? 288 : 144, cudaMemcpyDeviceToHost, s));
+    DG_CUDA(cudaMemcpyAsync(out_h_acc_jac, d_res + 288 * njobs, 144, cudaMemcpyDeviceToHost, s));
+    DG_CUDA(cudaStreamSynchronize(s));
+    for (size_t j = 0; j <= njobs && j < 32; j++) bad |= t.err_flag_host[1 + j];
+    if (bad) return fail(DG_ERR_BAD_ARG, "groth16_prove_msms: assignment element is not a reduced Montgomery residue");
     return DG_OK;
 }
 

@@ -33,6 +33,7 @@ EXPORTS = [
     'dg_gt_pow', 'dg_fp12_mul',
     'dg_fold_g1', 'dg_fold_g1_device', 'dg_fold_g2',
     'dg_fr_ntt', 'dg_fr_ntt_device', 'dg_qap_h_from_abc', 'dg_fr_spmv',
+    'dg_r1cs_upload', 'dg_r1cs_free', 'dg_groth16_prove_msms',
     'dg_g1_serialize', 'dg_g2_serialize', 'dg_g1_deserialize', 'dg_g2_deserialize',
     'dg_prof_enable', 'dg_prof_read_accumulate',
     'dg_dbg_fp_op', 'dg_dbg_fr_op', 'dg_dbg_set_tunable',
@@ -463,6 +464,50 @@ def fr_spmv(row_ptr, col, coeff_mont, w_mont):
     _check(lib.dg_fr_spmv(C.c_void_p(rp.ctypes.data), C.c_void_p(cl.ctypes.data), cop, C.c_size_t(rows), C.c_size_t(nnz), wp,
                           C.c_size_t(ncols), op))
     return o[:32 * rows]
+
+
+class R1CS:
+    """Device-resident constraint matrices (dg_r1cs_upload).  `mats` = three (row_ptr, col, coeff_mont) CSR triples."""
+
+    def __init__(self, mats, num_constraints, num_inputs, num_vars):
+        lib = init()
+        keep = []
+        rp, cl, co = (C.c_void_p * 3)(), (C.c_void_p * 3)(), (C.c_void_p * 3)()
+        for k, (r, c, v) in enumerate(mats):
+            r = np.ascontiguousarray(r, dtype=np.uint32)
+            c = np.ascontiguousarray(c, dtype=np.uint32)
+            v = _in(v)[0]
+            if r.size != num_constraints + 1 or c.size != int(r[-1]) or v.size != 32 * c.size:
+                raise ValueError('R1CS: malformed CSR matrix %d' % k)
+            keep += [r, c, v]
+            rp[k], cl[k], co[k] = r.ctypes.data, c.ctypes.data, v.ctypes.data
+        h = C.c_uint64(0)
+        _check(lib.dg_r1cs_upload(rp, cl, co, C.c_size_t(num_constraints), C.c_size_t(num_inputs), C.c_size_t(num_vars), C.byref(h)))
+        self.handle, self.num_constraints, self.num_inputs, self.num_vars = h.value, num_constraints, num_inputs, num_vars
+
+    def free(self):
+        if self.handle:
+            _check(load().dg_r1cs_free(C.c_uint64(self.handle)))
+            self.handle = 0
+
+
+def groth16_prove_msms(r1cs, full_assignment_mont, h_query, jobs, want_h=False):
+    """dg_groth16_prove_msms: jobs = [(Bases, scalar offset, count)].  -> (h_acc Jacobian, [job results], h or None)."""
+    lib = init()
+    w, wp = _in(full_assignment_mont)
+    nvars = w.size // 32
+    nj = len(jobs)
+    jb = (C.c_uint64 * max(nj, 1))(*[j[0].handle for j in jobs])
+    jo = (C.c_uint64 * max(nj, 1))(*[j[1] for j in jobs])
+    jc = (C.c_uint64 * max(nj, 1))(*[j[2] for j in jobs])
+    o_h, o_hp = _out(G1_JAC)
+    o_j, o_jp = _out(G2_JAC * max(nj, 1))
+    logn = max((r1cs.num_constraints + r1cs.num_inputs - 1).bit_length(), 0)
+    hm, hmp = _out(32 << logn) if want_h else (None, None)
+    _check(lib.dg_groth16_prove_msms(C.c_uint64(r1cs.handle), wp, C.c_size_t(nvars), C.c_uint64(h_query.handle), jb, jo, jc,
+                                     C.c_size_t(nj), o_hp, o_jp, hmp))
+    res = [o_j[G2_JAC * i:G2_JAC * i + (G2_JAC if jobs[i][0].g2 else G1_JAC)] for i in range(nj)]
+    return o_h[:G1_JAC], res, hm
 
 
 # ---- ark-serialize wire formats ------------------------------------------------------------------

@@ -215,6 +215,27 @@ int32_t dg_qap_h_from_abc(const uint8_t *a, const uint8_t *b, const uint8_t *c, 
 int32_t dg_fr_spmv(const uint32_t *row_ptr, const uint32_t *col, const uint8_t *coeff_mont, size_t rows, size_t nnz,
                    const uint8_t *w_mont, size_t ncols, uint8_t *out_mont);
 
+/* ---- device-chained LegoGroth16 prover (rows a18 + f1) ---------------------------------------------------------
+ * The constraint matrices of a circuit (ark_relations ConstraintMatrices a, b, c as CSR with Fr Montgomery
+ * coefficients; crypto_b200/r1cs.py produces this layout from a Circom .r1cs file) are uploaded once, next to the
+ * proving key's bases.  row_ptr / col / coeff_mont each point at three arrays (a, b, c): row_ptr[k] has
+ * num_constraints + 1 entries, col[k] / coeff_mont[k] have row_ptr[k][num_constraints] entries. */
+int32_t dg_r1cs_upload(const uint32_t *const row_ptr[3], const uint32_t *const col[3], const uint8_t *const coeff_mont[3],
+                       size_t num_constraints, size_t num_inputs, size_t num_vars, uint64_t *r1cs_handle);
+int32_t dg_r1cs_free(uint64_t r1cs_handle);
+/* create_proof_and_committed_witnesses_with_assignment's heavy half (legogroth16/src/prover.rs:267-383) for one full
+ * assignment (instance then witness variables, Fr Montgomery, full_assignment[0] = 1), chained on the device:
+ *   h = LibsnarkReduction::witness_map_from_matrices(...)           (r1cs_to_qap.rs:150-210)
+ *   out_h_acc_jac = msm_bigint(h_query, h.into_bigint())             (prover.rs:281-286); h never visits the host
+ *   out_jobs_jac[j] = msm_bigint(job_bases[j], assignment.into_bigint()[job_offset[j] .. job_offset[j] + job_count[j]])
+ *                     for the l_query / a_query / b_g1_query / b_g2_query / gamma_abc MSMs (prover.rs:299,326,334,344,363);
+ *                     each result sits in a 288-byte slot (G1 results use the first 144 bytes).
+ * job_bases are dg_bases_upload_g1 / _g2 handles (optionally precomputed).  out_h_mont (may be NULL) receives the
+ * 2^k coefficients of h for callers that want them. */
+int32_t dg_groth16_prove_msms(uint64_t r1cs_handle, const uint8_t *full_assignment_mont, size_t num_vars, uint64_t h_query_handle,
+                              const uint64_t *job_bases, const uint64_t *job_offset, const uint64_t *job_count, size_t njobs,
+                              uint8_t *out_h_acc_jac, uint8_t *out_jobs_jac, uint8_t *out_h_mont);
+
 /* ---- ark-serialize wire formats ("next" row f4 of SURVEY.md 8f) ------------------------------------
  * CanonicalSerialize::serialize_compressed / serialize_uncompressed and CanonicalDeserialize::
  * deserialize_compressed / deserialize_uncompressed for vectors of BLS12-381 points, as the reference
