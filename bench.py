@@ -553,7 +553,12 @@ def run_ours(args, rank, world, local_rank):
         line['cpu_baseline'] = {'value': n / dt, 'unit': UNIT, 'cores': cores, 'kind': 'port',
                                 'sample': 'best of 2 full 2^%d-term MSMs, oracle C restatement of ark-ec 0.4 '
                                           'msm_bigint_wnaf (OpenMP over windows)' % args.logn}
-    print(json.dumps(line), flush=True)
+    out = _REAL_STDOUT or sys.stdout
+    out.write(json.dumps(line) + '\n')
+    out.flush()
+
+
+_REAL_STDOUT = None
 
 
 def main():
@@ -580,6 +585,11 @@ def main():
     if world == 1:
         use_all_host_cores()                 # the cpu_baseline leg; before anything loads libgomp
     if world > 1:
+        # NCCL prints its version banner on stdout; keep stdout for the one JSON line (everything else -> stderr)
+        global _REAL_STDOUT
+        sys.stdout.flush()
+        _REAL_STDOUT = os.fdopen(os.dup(1), 'w')
+        os.dup2(2, 1)
         import torch
         import torch.distributed as dist
         os.environ.setdefault('MASTER_ADDR', '127.0.0.1')

@@ -14,7 +14,8 @@ __global__ void __launch_bounds__(128) k_dbg_fp_op(int op, const Fp *a, const Fp
         case 3: r = fp_sqr(x); break;
         case 4: r = fp_neg(x); break;
         case 5: r = fp_inv(x); break;            // Fermat a^(p-2)
-        case 6: r = fp_inv_binary(x); break;     // binary extended Euclid (the one the kernels use)
+        case 6: r = fp_inv_binary(x); break;     // bit-serial binary extended Euclid
+        case 7: r = fp_inv_pornin(x); break;     // Pornin's binary GCD with 31-bit inner rounds (the one the kernels use)
         default: r = fp_zero();
     }
     fp_store(&out[i], r);

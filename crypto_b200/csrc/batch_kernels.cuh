@@ -33,9 +33,9 @@ static __device__ __noinline__ Fp fp_inv(const Fp &a) {
     }
     return acc;
 }
-__device__ __forceinline__ Fp finv(const Fp &a) { return fp_inv_binary(a); }
+__device__ __forceinline__ Fp finv(const Fp &a) { return fp_inv_pornin(a); }
 __device__ __forceinline__ Fp2 finv(const Fp2 &a) {
-    Fp n = fp_inv_binary(fp_add(fp_mul_ni(a.c0, a.c0), fp_mul_ni(a.c1, a.c1)));
+    Fp n = fp_inv_pornin(fp_add(fp_mul_ni(a.c0, a.c0), fp_mul_ni(a.c1, a.c1)));
     return {fp_mul_ni(a.c0, n), fp_neg(fp_mul_ni(a.c1, n))};
 }
 

@@ -227,7 +227,7 @@ __device__ void f12_inv(Engine &e, F12 *d, const F12 *s, F12 *t0, F12 *t1, F12 *
     f12_mul(e, t1, t1, d);           // Norm in Fp2: only the w^0 coefficient is non-zero
     if (tid == 0) {
         Fp x = t1->c[0], y = t1->c[1];
-        Fp n = fp_inv_binary(fp_add(fp_mul(x, x), fp_mul(y, y)));
+        Fp n = fp_inv_pornin(fp_add(fp_mul(x, x), fp_mul(y, y)));
         t1->c[0] = fp_mul(x, n);
         t1->c[1] = fp_neg(fp_mul(y, n));
     }

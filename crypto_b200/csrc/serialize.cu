@@ -67,7 +67,7 @@ static __device__ __noinline__ bool fp2_sqrt(const Fp2 &a, Fp2 &out) {
         Fp d = fp_halve(k == 0 ? fp_add(a.c0, n) : fp_sub(a.c0, n));               // halving commutes with the Montgomery factor
         Fp s;
         if (!fp_sqrt(d, s) || fp_is_zero(s)) continue;
-        Fp c1 = sfp_mul(a.c1, fp_inv_binary(fp_dbl(s)));
+        Fp c1 = sfp_mul(a.c1, fp_inv_pornin(fp_dbl(s)));
         out = {s, c1};
         if (feq(fsqr(out), a)) return true;
     }

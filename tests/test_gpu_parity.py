@@ -36,10 +36,14 @@ def test_fp_ops_vs_bigint(dg, op):
     assert out == exp
 
 
-@pytest.mark.parametrize('op', [5, 6])          # 5: Fermat, 6: binary extended Euclid
+@pytest.mark.parametrize('op', [5, 6, 7])       # 5: Fermat, 6: bit-serial binary Euclid, 7: Pornin's binary GCD (31-bit inner rounds)
 def test_fp_inverse(dg, op):
     rng = np.random.default_rng(7)
-    xs = [1, 2, o.P - 1, 0x1234567890ABCDEF, 0, 3, (o.P + 1) // 2] + [int.from_bytes(rng.bytes(48), 'little') % o.P for _ in range(200)]
+    xs = [1, 2, o.P - 1, 0x1234567890ABCDEF, 0, 3, (o.P + 1) // 2, o.P - 2, (o.P - 1) // 2, 1 << 380, (1 << 381) % o.P, (1 << 64) - 1,
+          1 << 64, (1 << 96) + 1, 0xffffffff, 1 << 31, (1 << 31) - 1, 1 << 32, 1 << 33, (1 << 381) - 1 - o.P]
+    xs += [1 << k for k in range(0, 381, 7)] + [(o.P - (1 << k)) % o.P for k in range(0, 381, 11)]
+    xs += [int.from_bytes(rng.bytes(48), 'little') % o.P for _ in range(2000)]
+    xs += [int.from_bytes(rng.bytes(k), 'little') for k in (1, 4, 8, 9, 16, 24, 40)]
     a = b''.join(o.fp_to_mont_bytes(x) for x in xs)
     out = bytes(dg.dbg_fp_op(op, a, a))
     exp = b''.join(o.fp_to_mont_bytes(pow(x, o.P - 2, o.P)) for x in xs)
