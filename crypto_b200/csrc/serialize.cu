@@ -13,6 +13,13 @@
 // method (Fp2), root selection by the sort flag.  Subgroup membership by the endomorphism tests
 // ark-bls12-381 itself uses (eprint 2021/1130 section 6):  G1  (beta x, y) == -[x^2] P,
 // G2  psi(Q) == [x] Q; the oracle checks both against the definition [r] P == O.
+//
+// Deliberately STRICTER than ark-bls12-381 0.4 on malformed input (arkworks' source is not in /root/reference, so its
+// behaviour here is as recalled, not verified): (1) an encoding with the infinity flag must have an all-zero body and
+// no sort flag -- arkworks is believed to return the identity without looking at the body; (2) an uncompressed point
+// must satisfy the curve equation even with validate == 0 -- arkworks is believed to build it with new_unchecked and
+// test the curve and the subgroup only under Validate::Yes.  Every encoding arkworks itself PRODUCES round-trips
+// identically; the differences only reject byte strings no serializer emits.  tests/test_wire_formats.py pins both.
 #include "common.cuh"
 #include "ec.cuh"
 #include "fp_inv.cuh"

@@ -336,6 +336,8 @@ def batch_mul_add_fixed_g1(points, scalars_a, table, scalars_b):
     lib = init()
     p, pp = _in(points); a, ap = _in(scalars_a); b, bp = _in(scalars_b)
     m = a.size // SCALAR
+    if a.size % SCALAR or b.size != a.size or p.size != G1_AFF * m:
+        raise ValueError('batch_mul_add_fixed_g1: points, scalars_a and scalars_b must describe the same number of elements')
     o, op = _out(G1_AFF * m)
     _check(lib.dg_batch_mul_add_fixed_g1(pp, ap, C.c_uint64(table.handle), bp, C.c_size_t(m), op))
     return o[:G1_AFF * m]
@@ -459,6 +461,8 @@ def fr_spmv(row_ptr, col, coeff_mont, w_mont):
     cl = np.ascontiguousarray(col, dtype=np.uint32)
     co, cop = _in(coeff_mont)
     w, wp = _in(w_mont)
+    if rp.size < 1 or w.size % 32 or co.size != 32 * cl.size:
+        raise ValueError('fr_spmv: row_ptr must be non-empty, w a multiple of 32 bytes and coeff_mont 32 bytes per column index')
     rows, nnz, ncols = rp.size - 1, cl.size, w.size // 32
     o, op = _out(32 * rows)
     _check(lib.dg_fr_spmv(C.c_void_p(rp.ctypes.data), C.c_void_p(cl.ctypes.data), cop, C.c_size_t(rows), C.c_size_t(nnz), wp,

@@ -108,7 +108,10 @@ class R1CSFile:
         for _ in range(_u32(reader)):
             t, size = _u32(reader), _u64(reader)
             offsets[t], sizes[t] = reader.tell(), size
-            reader.seek(size, io.SEEK_CUR)
+            try:
+                reader.seek(size, io.SEEK_CUR)
+            except (OverflowError, OSError, ValueError):
+                raise _parsing('Invalid section size') from None
         for t, name in ((1, 'header'), (2, 'constraint'), (3, 'wire2label')):
             if t not in offsets:
                 raise _parsing('No section offset for %s type found' % name)
@@ -120,6 +123,8 @@ class R1CSFile:
         if sizes[3] != header.n_wires * 8:
             raise _parsing('Invalid map section size')
         wire_mapping = [_u64(reader) for _ in range(header.n_wires)]
+        if wire_mapping and wire_mapping[0] != 0:                    # read_map, r1cs_reader.rs:233
+            raise _parsing('Wire 0 should always be mapped to 0')
         return cls(version, header, constraints, wire_mapping)
 
     # ---- derived views ------------------------------------------------------------------------------------

@@ -246,7 +246,9 @@ int32_t dg_groth16_prove_msms(uint64_t r1cs_handle, const uint8_t *full_assignme
  * Validate::Yes.  status (n bytes, may be NULL): 0 ok, 1 malformed (compression flag, coordinate >= p,
  * stray bits), 2 not on the curve, 3 not in the prime-order subgroup; rejected elements come back as the
  * identity record and are counted in *invalid_count (may be NULL) -- ark returns Err for the whole
- * vector when the count is non-zero. */
+ * vector when the count is non-zero.  Stricter than ark-bls12-381 0.4 (as recalled; see csrc/serialize.cu) on two kinds
+ * of malformed input no serializer emits: an infinity encoding with a non-zero body is status 1, and an uncompressed
+ * point off the curve is status 2 even with validate == 0. */
 int32_t dg_g1_serialize(const uint8_t *affine, size_t n, int32_t compressed, uint8_t *out);
 int32_t dg_g2_serialize(const uint8_t *affine, size_t n, int32_t compressed, uint8_t *out);
 int32_t dg_g1_deserialize(const uint8_t *in, size_t n, int32_t compressed, int32_t validate, uint8_t *out_affine, uint8_t *status,

@@ -53,6 +53,8 @@ def test_sections_in_any_order():
     (lambda d: d[:24] + struct.pack('<I', 31) + d[28:], 'This parser only supports 32-byte fields'),
     (lambda d: d[:16] + struct.pack('<Q', 65) + d[24:88] + b'\x00' + d[88:], 'Invalid header section size'),
     (lambda d: d[:-5], 'failed to fill whole buffer'),
+    (lambda d: d[:len(d) - 8 * 5] + struct.pack('<Q', 1) + d[len(d) - 8 * 5 + 8:], 'Wire 0 should always be mapped to 0'),
+    (lambda d: d[:16] + struct.pack('<Q', 1 << 63) + d[24:], 'Invalid section size'),
 ])
 def test_rejections_match_the_reference_reader(mutate, msg):
     data, _ = squaring_chain(3)
