@@ -478,12 +478,13 @@ def run_ours(args, rank, world, local_rank):
     achieved = alg_bytes / (dom_ms * 1e-3) / 1e9 if dom_ms else None
     ip = load_json(os.path.join(ROOT, 'profiles', 'int_peak_r01.json')) or {}
     imad_peak = (ip.get('imad_lo') or {}).get('ops_per_s')
+    from crypto_b200 import msm as msm_mirror
     c_plain, rounds = lib.msm_plan(n)
-    ndig = (254 + c_plain - 1) // c_plain + (1 if 254 % c_plain == 0 else 0)        # msm_ndigits
+    ndig = msm_mirror.msm_digits_per_scalar(c_plain, plain_bases=True)              # GLV: 2 x ceil(128 / c) digits per scalar
     # The dominant kernel of the `value` path: with batch-affine rounds it is round 0 (k_affine_round<Fp, gather>), which
     # visits every (scalar digit, base) entry once and performs half of them as affine additions; without rounds k_accumulate.
     if rounds:
-        dom_kernel = 'k_affine_round<Fp, gather> (round 0 of %d, raw bases, c = %d, %d windows)' % (rounds, c_plain, ndig)
+        dom_kernel = 'k_affine_round<Fp, gather> (round 0 of %d, raw bases + GLV, c = %d, %d digits per scalar)' % (rounds, c_plain, ndig)
         ncu = load_json(os.path.join(ROOT, 'profiles', 'ncu_affine_round_plain_r02.json')) or \
             load_json(os.path.join(ROOT, 'profiles', 'ncu_affine_round.json')) or {}
         adds, mults_per_add = n * ndig / 2.0, 6.0          # 5M + 1S per affine addition incl. the shared inversion

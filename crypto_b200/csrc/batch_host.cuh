@@ -204,6 +204,7 @@ template <class F> static int32_t bases_precompute(HandleRec &rec, int c, cudaSt
     rec.dev = table;
     rec.window = c;
     rec.nwin = rows;
+    rec.phi_off = 0;                                       // the table replaces the GLV-expanded plain array
     return DG_OK;
 }
 

@@ -199,13 +199,13 @@ static int32_t msm_host(uint64_t handle, const uint8_t *bases, const uint8_t *sc
     if ((handle != 0) == (bases != nullptr) && n) return fail(DG_ERR_BAD_ARG, "msm: give exactly one of bases_handle / bases");
     ThreadState &t = tls();
     const void *bases_dev = nullptr;
-    MsmPre pre = {0, 0};
+    MsmPre pre = {0, 0, 0};
     if (handle) {
         HandleRec rec;
         rc = lookup_bases<G2>(handle, n, "msm", rec);
         if (rc) return rc;
         bases_dev = rec.dev;
-        if (rec.window) pre = {rec.window, (uint32_t)rec.n};
+        pre = msm_pre_of(rec);
     }
     size_t need = (G2 ? msm_scratch_bytes_g2(n, pre) : msm_scratch_bytes_g1(n, pre)) + Arena::pad(32 * n) + Arena::pad(JAC) +
                   (handle ? 0 : Arena::pad(PT * n));
@@ -235,13 +235,13 @@ template <bool G2>
 static int32_t msm_device(uint64_t handle, const void *bases_dev, const void *scalars_dev, size_t n, void *out_jac_dev, void *stream) {
     int32_t rc = check_init();
     if (rc) return rc;
-    MsmPre pre = {0, 0};
+    MsmPre pre = {0, 0, 0};
     if (handle) {
         HandleRec rec;
         rc = lookup_bases<G2>(handle, n, "msm_device", rec);
         if (rc) return rc;
         bases_dev = rec.dev;
-        if (rec.window) pre = {rec.window, (uint32_t)rec.n};
+        pre = msm_pre_of(rec);
     }
     if (!out_jac_dev || (n && (!bases_dev || !scalars_dev))) return fail(DG_ERR_BAD_ARG, "msm_device: null pointer");
     ThreadState &t = tls();
@@ -261,17 +261,21 @@ template <bool G2> static int32_t bases_upload(const uint8_t *affine, size_t n, 
     if (rc) return rc;
     if (!affine || !handle || n == 0) return fail(DG_ERR_BAD_ARG, "bases_upload: null pointer or n == 0");
     const size_t PT = G2 ? 192 : 96;
+    if (n >= (1ull << 30)) return fail(DG_ERR_BAD_ARG, "bases_upload: n must be < 2^30");
+    // The resident array holds the points followed by their GLV images phi(P_i) = (beta x_i, y_i) (one field
+    // multiplication per point, done here once instead of inside every MSM).
     void *dev = nullptr;
-    DG_CUDA(cudaMalloc(&dev, PT * n));
+    DG_CUDA(cudaMalloc(&dev, 2 * PT * n));
     ThreadState &t = tls();
     cudaError_t e = cudaMemcpyAsync(dev, affine, PT * n, cudaMemcpyHostToDevice, t.stream);
+    if (e == cudaSuccess && (G2 ? glv_expand_g2(dev, n, dev, n, t.stream) : glv_expand_g1(dev, n, dev, n, t.stream)) != DG_OK) e = cudaErrorUnknown;
     if (e == cudaSuccess) e = cudaStreamSynchronize(t.stream);
     if (e != cudaSuccess) { cudaFree(dev); return fail(DG_ERR_CUDA, cudaGetErrorString(e)); }
     std::lock_guard<std::mutex> lk(ctx().mu);
     uint64_t h = ctx().next_handle++;
     HandleRec r;
     r.kind = G2 ? HandleRec::BASES_G2 : HandleRec::BASES_G1;
-    r.dev = dev; r.n = n; r.slot = t.slot;
+    r.dev = dev; r.n = n; r.slot = t.slot; r.phi_off = n;
     ctx().handles[h] = r;
     *handle = h;
     return DG_OK;
@@ -622,7 +626,7 @@ int32_t dg_msm_plan(size_t n, int32_t is_g2, int32_t precomputed_window_bits, in
     int32_t rc = check_init();
     if (rc) return rc;
     if (!window_bits || !affine_rounds) return fail(DG_ERR_BAD_ARG, "msm_plan: null pointer");
-    MsmPre pre = {precomputed_window_bits, precomputed_window_bits ? (uint32_t)n : 0u};
+    MsmPre pre = {precomputed_window_bits, precomputed_window_bits ? (uint32_t)n : 0u, 0u};
     int c = 0, r = 0;
     if (is_g2) msm_plan_g2(n, pre, &c, &r); else msm_plan_g1(n, pre, &c, &r);
     *window_bits = c;

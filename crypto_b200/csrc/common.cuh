@@ -26,6 +26,7 @@ struct HandleRec {
     size_t n = 0;            // bases: point count; tables: total records
     int window = 0, nwin = 0;   // tables: window geometry; bases: precompute window / rows (0 = plain)
     int slot = 0;            // index into Context::devices of the GPU that owns `dev`
+    size_t phi_off = 0;      // plain bases: dev holds 2 n records, phi(P_i) = (beta x_i, y_i) at phi_off + i (GLV, msm_kernels.cuh)
     // SHARDED_*: one contiguous base range per device of dg_init_devices; shard d covers
     // [shard_lo[d], shard_lo[d + 1]) and lives behind the ordinary single-device handle shard_handle[d]
     std::vector<uint64_t> shard_handle;
@@ -132,7 +133,16 @@ static inline unsigned div_up(size_t a, size_t b) { return (unsigned)((a + b - 1
 // ---- internal entry points implemented per translation unit (device pointers, async) ----------
 // Precomputed-bases descriptor: c = 0 means plain bases; otherwise the table holds ceil(256/c)
 // rows of row_stride affine points, row k = 2^(c*k) * P_i (dg_bases_precompute).
-struct MsmPre { int c; uint32_t row_stride; };
+// phi_off != 0 (plain bases only): the array already holds the GLV images phi(P_i) at index phi_off + i (resident handles
+// are expanded once at upload); 0 = msm_run expands the bases into its scratch first.
+struct MsmPre { int c; uint32_t row_stride; uint32_t phi_off; };
+static inline MsmPre msm_pre_of(const HandleRec &r) {
+    return r.window ? MsmPre{r.window, (uint32_t)r.n, 0u} : MsmPre{0, 0u, (uint32_t)r.phi_off};
+}
+// digits per GLV half-scalar (k < 2^127): the top digit stays below 2^(c-1) even with the carry
+static inline int glv_ndigits(int c) { return (128 + c - 1) / c; }
+int32_t glv_expand_g1(const void *in, size_t n, void *out, size_t phi_off, cudaStream_t s);      // msm_g1.cu
+int32_t glv_expand_g2(const void *in, size_t n, void *out, size_t phi_off, cudaStream_t s);      // msm_g2.cu
 // Signed radix-2^c digits per scalar.  k_digits first maps a canonical scalar s to min(s, r - s) < 2^254 (negating
 // the point), so ceil(254 / c) digits suffice: the top digit is narrower than c bits and stays <= 2^(c-1) even with
 // the carry -- except when c divides 254, where it is full width and its carry needs one more digit.

@@ -11,4 +11,9 @@ int32_t msm_run_g1(const void *bases_dev, const void *scalars_dev, size_t n, voi
                    uint32_t *err_flag, cudaStream_t s, MsmPre pre) {
     return msm_run<Fp>(bases_dev, scalars_dev, n, out_jac_dev, scratch, err_flag, s, pre);
 }
+int32_t glv_expand_g1(const void *in, size_t n, void *out, size_t phi_off, cudaStream_t s) {
+    if (n) DG_LAUNCH(k_glv_expand<Fp>, div_up(n, 256), 256, 0, s, (const Affine<Fp> *)in, (uint32_t)n, (Affine<Fp> *)out, (uint32_t)phi_off);
+    DG_CUDA(cudaGetLastError());
+    return DG_OK;
+}
 }  // namespace dg

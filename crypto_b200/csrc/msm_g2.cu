@@ -12,4 +12,9 @@ int32_t msm_run_g2(const void *bases_dev, const void *scalars_dev, size_t n, voi
                    uint32_t *err_flag, cudaStream_t s, MsmPre pre) {
     return msm_run<Fp2>(bases_dev, scalars_dev, n, out_jac_dev, scratch, err_flag, s, pre);
 }
+int32_t glv_expand_g2(const void *in, size_t n, void *out, size_t phi_off, cudaStream_t s) {
+    if (n) DG_LAUNCH(k_glv_expand<Fp2>, div_up(n, 256), 256, 0, s, (const Affine<Fp2> *)in, (uint32_t)n, (Affine<Fp2> *)out, (uint32_t)phi_off);
+    DG_CUDA(cudaGetLastError());
+    return DG_OK;
+}
 }  // namespace dg

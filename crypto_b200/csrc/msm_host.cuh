@@ -22,12 +22,15 @@ static inline MsmGeom msm_geometry(size_t n, MsmPre pre) {
     }
     MsmGeom g;
     g.c = c;
-    g.ndig = msm_ndigits(c);
+    // plain bases: GLV split (tunable 4 != 0 switches it off, for A/B measurements and tests of the unsplit path)
+    g.glv = (!pre.c && ctx().tunable[4].load() == 0) ? 1 : 0;
+    g.ndig = g.glv ? glv_ndigits(c) : msm_ndigits(c);
     g.nwin = pre.c ? 1 : g.ndig;
     g.nbw = 1u << (c - 1);
     g.nb = g.nbw * (uint32_t)g.nwin;
     g.row_stride = pre.c ? pre.row_stride : 0;
     g.fp2 = 0;
+    g.phi_off = 0;
     return g;
 }
 
@@ -35,7 +38,7 @@ static inline MsmGeom msm_geometry(size_t n, MsmPre pre) {
 struct MsmLayout {
     MsmGeom g;
     uint32_t L, nchunks, red_stride;
-    size_t o_hist, o_off, o_cursor, o_bsums, o_entries, o_buckets, o_head, o_tail, o_long, o_longpart, o_red[4], total;
+    size_t o_hist, o_off, o_cursor, o_bsums, o_entries, o_buckets, o_head, o_tail, o_long, o_longpart, o_red[4], o_glv, total;
     // batch-affine pre-reduction (msm_affine.cuh): R rounds, round r turns <= mb[r] points into <= mb[r + 1]
     int R;
     uint64_t mb[DG_BA_MAX_ROUNDS + 1];
@@ -51,7 +54,7 @@ static inline int msm_affine_rounds(size_t n, const MsmGeom &g) {
     if (ov >= 0) return ov > DG_BA_MAX_ROUNDS ? DG_BA_MAX_ROUNDS : ov;
     // measured (tools/sweep_rounds.py): a round pays while the buckets still hold >= 6 points and it
     // has >= 2^20 (G1) / 2^18 (G2) additions to spread over the grid
-    double entries = (double)n * g.ndig, load = entries / (double)g.nb;     // average points per bucket
+    double entries = (double)n * g.ndig * (g.glv ? 2 : 1), load = entries / (double)g.nb;     // average points per bucket
     int r = 0;
     const double min_adds = g.fp2 ? 262144.0 : 1048576.0;              // an Fp2 addition is ~3x the work: smaller rounds still pay
     while (r < DG_BA_MAX_ROUNDS && load >= 6.0 && entries * 0.5 >= min_adds) { load *= 0.5; entries *= 0.5; r++; }
@@ -62,7 +65,7 @@ template <class F> static inline MsmLayout msm_layout(size_t n, MsmPre pre) {
     MsmLayout m;
     m.g = msm_geometry(n, pre);
     m.g.fp2 = sizeof(F) > 48;
-    size_t max_entries = n * (size_t)m.g.ndig;
+    size_t max_entries = n * (size_t)m.g.ndig * (m.g.glv ? 2 : 1);
     m.R = msm_affine_rounds(n, m.g);
     m.mb[0] = max_entries;
     for (int r = 0; r < m.R; r++) m.mb[r + 1] = (m.mb[r] + m.g.nb) / 2 + 1;     // sum_b ceil(n_b / 2) <= (M + nb) / 2
@@ -109,6 +112,8 @@ template <class F> static inline MsmLayout msm_layout(size_t n, MsmPre pre) {
         m.o_red[2] = take(sizeof(XYZZ<F>) * (size_t)m.g.nwin);
         m.o_red[3] = m.o_red[2];
     }
+    m.o_glv = 0;
+    if (m.g.glv && !pre.phi_off) m.o_glv = take(sizeof(Affine<F>) * 2 * (n ? n : 1));     // [P | phi(P)] built per call
     m.o_cnt = m.cnt_stride = m.o_pre = m.o_rbsums = m.rbs_stride = 0;
     m.o_aff[0] = m.o_aff[1] = 0;
     if (m.R) {
@@ -144,11 +149,26 @@ static int32_t msm_run(const void *bases_dev, const void *scalars_dev, size_t n,
         return DG_OK;
     }
     if (n >= (1ull << 31)) return fail(DG_ERR_BAD_ARG, "msm: n must be < 2^31");
-    if ((uint64_t)n * msm_geometry(n, pre).ndig >= 0xffffffffull)
-        return fail(DG_ERR_BAD_ARG, "msm: n * digits must fit 32-bit entry offsets (n up to ~2^27)");
+    {
+        MsmGeom g0 = msm_geometry(n, pre);
+        if ((uint64_t)n * g0.ndig * (g0.glv ? 2 : 1) >= 0xffffffffull)
+            return fail(DG_ERR_BAD_ARG, "msm: n * digits must fit 32-bit entry offsets (n up to ~2^27)");
+        if (g0.glv && (uint64_t)n + (pre.phi_off ? pre.phi_off : n) >= (1ull << 31))
+            return fail(DG_ERR_BAD_ARG, "msm: n must be < 2^30 for plain bases");
+    }
     if (pre.c && (uint64_t)pre.row_stride * msm_ndigits(pre.c) >= (1ull << 31))
         return fail(DG_ERR_BAD_ARG, "msm: precomputed table too large for 31-bit point indices");
     MsmLayout m = msm_layout<F>(n, pre);
+    if (m.g.glv) {
+        if (pre.phi_off) {
+            m.g.phi_off = pre.phi_off;
+        } else {                                           // raw bases: build [P | phi(P)] in the scratch first
+            Affine<F> *ex = (Affine<F> *)(scratch + m.o_glv);
+            DG_LAUNCH(k_glv_expand<F>, div_up(n, 256), 256, 0, s, (const Affine<F> *)bases_dev, (uint32_t)n, ex, (uint32_t)n);
+            bases_dev = ex;
+            m.g.phi_off = (uint32_t)n;
+        }
+    }
     const MsmGeom g = m.g;
     uint32_t *hist = (uint32_t *)(scratch + m.o_hist), *off = (uint32_t *)(scratch + m.o_off);
     uint32_t *cursor = (uint32_t *)(scratch + m.o_cursor), *bsums = (uint32_t *)(scratch + m.o_bsums);

@@ -463,7 +463,7 @@ int32_t dg_groth16_prove_msms(uint64_t r1cs_handle, const uint8_t *full_assignme
     if (jb[njobs].kind != HandleRec::BASES_G1) return fail(DG_ERR_BAD_ARG, "groth16_prove_msms: h_query must be G1");
     const size_t nh = jb[njobs].n < D ? jb[njobs].n : D;                        // msm_bigint truncates to the shorter side
     size_t msm_scratch = 0;
-    auto pre_of = [](const HandleRec &r) { return r.window ? MsmPre{r.window, (uint32_t)r.n} : MsmPre{0, 0}; };
+    auto pre_of = [](const HandleRec &r) { return msm_pre_of(r); };
     for (size_t j = 0; j <= njobs; j++) {
         size_t cnt = j < njobs ? job_count[j] : nh;
         if (j < njobs && (job_offset[j] > num_vars || cnt > num_vars - job_offset[j])) return fail(DG_ERR_BAD_ARG, "groth16_prove_msms: scalar range outside the assignment");

@@ -263,3 +263,38 @@ def msm_recode(s, c):
     if carry:
         raise AssertionError('top digit carried out: msm_ndigits(%d) is too small' % c)
     return flip, digits
+
+
+# ---- GLV split of the plain-bases path (specification mirror; csrc/msm_kernels.cuh glv_split) -----------------------
+BLS_X_ABS = 0xD201000000010000
+GLV_X2 = BLS_X_ABS * BLS_X_ABS                      # lambda = -x^2 mod r is the eigenvalue of phi(x, y) = (beta x, y)
+GLV_LAMBDA = (-GLV_X2) % R_MODULUS
+
+
+def glv_ndigits(c):
+    """Signed radix-2^c digits per 127-bit half-scalar."""
+    return (128 + c - 1) // c
+
+
+def glv_split(s):
+    """(sign1, k1, sign2, k2) with  s = sign1 * k1 + sign2 * k2 * lambda  (mod r)  and  k1, k2 < 2^127: the scalar is first
+    reduced to s' = min(s, r - s), then s' = q x^2 +- k1 with k1 <= x^2 / 2 (Barrett quotient by the constant x^2)."""
+    if not 0 <= s < R_MODULUS:
+        raise ValueError('scalar is not canonical (>= r)')
+    flip = R_MODULUS - s < s
+    sp = R_MODULUS - s if flip else s
+    q = (sp * ((1 << 256) // GLV_X2)) >> 256
+    rem = sp - q * GLV_X2
+    while rem >= GLV_X2:
+        rem -= GLV_X2
+        q += 1
+    neg1 = rem > GLV_X2 // 2
+    if neg1:
+        rem, q = GLV_X2 - rem, q + 1
+    sigma = -1 if flip else 1
+    return (-sigma if neg1 else sigma), rem, -sigma, q
+
+
+def msm_digits_per_scalar(c, plain_bases):
+    """Bucket entries a non-zero scalar contributes at most: 2 x glv_ndigits for plain bases, msm_ndigits through a table."""
+    return 2 * glv_ndigits(c) if plain_bases else msm_ndigits(c)

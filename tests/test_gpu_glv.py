@@ -1,0 +1,79 @@
+"""GPU: the GLV split of the plain-bases MSM path (csrc/msm_kernels.cuh glv_split / k_glv_expand): the same group
+element as the unsplit path, the oracle and the known-discrete-log identity, for G1 and G2, raw bases and resident plain
+handles, including the scalars where the split has its corner cases (multiples of x^2, x^2 / 2, lambda, r - 1 ...)."""
+import numpy as np
+import pytest
+
+from crypto_b200 import msm
+from tests import helpers as h
+
+pytestmark = pytest.mark.gpu
+
+R = msm.R_MODULUS
+EDGE = [0, 1, 2, R - 1, R - 2, (R - 1) // 2, (R + 1) // 2, msm.GLV_X2, msm.GLV_X2 - 1, msm.GLV_X2 + 1, msm.GLV_X2 // 2,
+        msm.GLV_X2 // 2 + 1, msm.GLV_LAMBDA, msm.GLV_LAMBDA + 1, R - msm.GLV_LAMBDA, 5 * msm.GLV_X2, 5 * msm.GLV_X2 + msm.GLV_X2 // 2 + 1,
+        (1 << 127), (1 << 127) - 1, (1 << 128) + 1, (1 << 254) - 1, 1 << 254]
+
+
+def _glv(dg, on):
+    dg.dbg_set_tunable(4, 0 if on else 1)
+
+
+@pytest.mark.parametrize('n', [1, 31, 33, 1000, 1 << 14, (1 << 17) + 5])
+def test_g1_glv_equals_unsplit_and_known_dlog(dg, cref, n):
+    bases, ks = h.g1_bases(n, 600 + n)
+    ss = np.array(h.rand_scalars(n, 601 + n))
+    edge = h.scalars_bytes([e % R for e in EDGE])[:32 * min(n, len(EDGE))]
+    ss[:len(edge)] = edge
+    exp = h.known_dlog_msm_g1(ks, ss)
+    try:
+        _glv(dg, True)
+        assert dg.msm_plan(n)[0] >= 4
+        got_glv = h.affine_g1(dg.msm(bases, ss))
+        hb = dg.Bases(bases)
+        got_handle = h.affine_g1(dg.msm(hb, ss))
+        got_prefix = h.affine_g1(dg.msm(hb, ss[:32 * (n // 2)])) if n > 1 else None
+        hb.free()
+        _glv(dg, False)
+        got_plain = h.affine_g1(dg.msm(bases, ss))
+    finally:
+        _glv(dg, True)
+    assert got_glv == got_plain == got_handle == exp
+    if n > 1:
+        assert got_prefix == h.known_dlog_msm_g1(ks[:32 * (n // 2)], ss[:32 * (n // 2)])
+    if n <= 1000:
+        assert got_glv == h.affine_g1(cref.msm_g1(bases, ss))
+
+
+@pytest.mark.parametrize('n', [1, 40, 3001])
+def test_g2_glv_equals_unsplit_and_known_dlog(dg, cref, n):
+    bases, ks = h.g2_bases(n, 700 + n)
+    ss = np.array(h.rand_scalars(n, 701 + n))
+    edge = h.scalars_bytes([e % R for e in EDGE])[:32 * min(n, len(EDGE))]
+    ss[:len(edge)] = edge
+    exp = h.known_dlog_msm_g2(ks, ss)
+    try:
+        _glv(dg, True)
+        got_glv = h.affine_g2(dg.msm(bases, ss, g2=True))
+        hb = dg.Bases(bases, g2=True)
+        got_handle = h.affine_g2(dg.msm(hb, ss, g2=True))
+        hb.free()
+        _glv(dg, False)
+        got_plain = h.affine_g2(dg.msm(bases, ss, g2=True))
+    finally:
+        _glv(dg, True)
+    assert got_glv == got_plain == got_handle == exp
+
+
+def test_glv_with_identity_equal_and_opposite_bases(dg, cref):
+    """phi maps the identity record to itself and commutes with negation: the adversarial base sets of the plain path."""
+    n = 64
+    bases, ks = h.g1_bases(n, 55)
+    b = bytearray(bytes(bases))
+    b[0:96] = bytes(96)                                  # identity
+    b[96 * 5:96 * 6] = b[96 * 4:96 * 5]                  # P, P
+    b[96 * 7:96 * 8] = h.neg_g1(bytes(b[96 * 6:96 * 7]))  # P, -P
+    ss = h.rand_scalars(n, 56)
+    assert h.affine_g1(dg.msm(bytes(b), ss)) == h.affine_g1(cref.msm_g1(np.frombuffer(bytes(b), dtype=np.uint8), ss))
+    same = np.frombuffer(bytes(b[96:192]) * n, dtype=np.uint8)       # every base equal: one hot bucket per window
+    assert h.affine_g1(dg.msm(same, ss)) == h.affine_g1(cref.msm_g1(same, ss))

@@ -79,3 +79,27 @@ def test_msm_digit_recoding_spec():
     import pytest
     with pytest.raises(ValueError):
         msm.msm_recode(r, 16)
+
+
+def test_glv_split_is_exact_and_short():
+    """The GLV mirror of k_digits: s == sign1 k1 + sign2 k2 lambda (mod r), both halves below 2^127, and their signed
+    digits never carry out of glv_ndigits(c) windows."""
+    import random
+    from crypto_b200 import msm
+    r, x2, lam = msm.R_MODULUS, msm.GLV_X2, msm.GLV_LAMBDA
+    assert (lam * lam + lam + 1) % r == 0
+    rng = random.Random(11)
+    cases = [0, 1, r - 1, (r - 1) // 2, (r + 1) // 2, x2, x2 - 1, x2 + 1, x2 // 2, x2 // 2 + 1, lam, lam + 1, r - lam, 3 * x2 + x2 // 2]
+    cases += [rng.randrange(r) for _ in range(3000)] + [rng.randrange(1 << k) for k in range(1, 255, 3)]
+    for s in cases:
+        s1, k1, s2, k2 = msm.glv_split(s)
+        assert (s1 * k1 + s2 * k2 * lam) % r == s and k1 < (1 << 127) and k2 < (1 << 127)
+        for c in (4, 11, 13, 16, 17, 20, 23):
+            for k in (k1, k2):
+                carry, half = 0, 1 << (c - 1)
+                for j in range(msm.glv_ndigits(c)):
+                    d = ((k >> (c * j)) & ((1 << c) - 1)) + carry
+                    carry = 1 if d > half else 0
+                assert carry == 0
+    with pytest.raises(ValueError):
+        msm.glv_split(r)
