@@ -21,6 +21,9 @@ ThreadState::~ThreadState() {
         arena.release();
         if (err_flag) cudaFree(err_flag);
         if (err_flag_host) cudaFreeHost(err_flag_host);
+        if (stream2) cudaStreamDestroy(stream2);
+        if (ev_a) cudaEventDestroy(ev_a);
+        if (ev_b) cudaEventDestroy(ev_b);
         cudaStreamDestroy(stream);
     }
 }

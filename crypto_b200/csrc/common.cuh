@@ -96,6 +96,8 @@ struct Arena {
 
 struct ThreadState {
     cudaStream_t stream = nullptr;
+    cudaStream_t stream2 = nullptr;   // second stream for calls that overlap independent MSMs (dg_groth16_prove_msms); created on first use
+    cudaEvent_t ev_a = nullptr, ev_b = nullptr;
     int slot = 0;                     // device slot this thread drives: 0 for callers, d for the worker of devices[d]
     Arena arena;
     std::string err;

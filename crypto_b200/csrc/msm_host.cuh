@@ -14,16 +14,26 @@ static inline int ceil_log2_sz(size_t n) { int l = 0; while (((size_t)1 << l) < 
 // accumulation work.  nwin * c >= 256 so the top signed digit cannot overflow.
 static inline MsmGeom msm_geometry(size_t n, MsmPre pre) {
     int c = pre.c ? pre.c : ctx().msm_window_override.load();
+    const bool glv = !pre.c && ctx().tunable[4].load() == 0;
     if (c <= 0) {
-        c = ceil_log2_sz(n ? n : 1) - 4;
-        if (c < 4) c = 4;
-        if (c > 20) c = 20;
-        if (c >= 13 && c <= 19) c = 16;   // measured on B200 (tools/sweep_c.py): 16 x 16 = 256 bits exactly wins from 2^17 to 2^23
+        const int logn = ceil_log2_sz(n ? n : 1);
+        if (glv) {
+            // measured on B200 with the GLV split (tools/sweep_rounds.py, 2^16 .. 2^24): 8 windows of 16 bits win from 2^17
+            // terms up to at least 2^24 (2^15 buckets per window keep the reduction small, 8 x 16 = 128 bits exactly);
+            // below that the window-combination chain dominates and about log2(n) - 3 bits are best
+            c = logn >= 17 ? 16 : logn - 3;
+            if (c < 4) c = 4;
+        } else {
+            c = logn - 4;
+            if (c < 4) c = 4;
+            if (c > 20) c = 20;
+            if (c >= 13 && c <= 19) c = 16;   // measured on B200 (tools/sweep_c.py): 16 x 16 = 256 bits exactly wins from 2^17 to 2^23
+        }
     }
     MsmGeom g;
     g.c = c;
     // plain bases: GLV split (tunable 4 != 0 switches it off, for A/B measurements and tests of the unsplit path)
-    g.glv = (!pre.c && ctx().tunable[4].load() == 0) ? 1 : 0;
+    g.glv = glv ? 1 : 0;
     g.ndig = g.glv ? glv_ndigits(c) : msm_ndigits(c);
     g.nwin = pre.c ? 1 : g.ndig;
     g.nbw = 1u << (c - 1);

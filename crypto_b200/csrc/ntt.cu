@@ -473,7 +473,16 @@ int32_t dg_groth16_prove_msms(uint64_t r1cs_handle, const uint8_t *full_assignme
     }
     ThreadState &t = tls();
     cudaStream_t s = t.stream;
-    size_t need = 2 * Arena::pad(32 * num_vars) + 4 * Arena::pad(32 * D) + Arena::pad(288 * (njobs + 1)) + Arena::pad(msm_scratch);
+    // Two streams: stream A runs the witness map and then MSMs, stream B starts on the assignment MSMs at once.  The
+    // latency-bound tail of one MSM (bucket reduction, window combination: ~1 ms of a 2^18-term MSM) then overlaps the
+    // throughput-bound body of another instead of idling the SMs.
+    if (!t.stream2) {
+        DG_CUDA(cudaStreamCreateWithFlags(&t.stream2, cudaStreamNonBlocking));
+        DG_CUDA(cudaEventCreateWithFlags(&t.ev_a, cudaEventDisableTiming));
+        DG_CUDA(cudaEventCreateWithFlags(&t.ev_b, cudaEventDisableTiming));
+    }
+    cudaStream_t st[2] = {s, t.stream2};
+    size_t need = 2 * Arena::pad(32 * num_vars) + 4 * Arena::pad(32 * D) + Arena::pad(288 * (njobs + 1)) + 2 * Arena::pad(msm_scratch);
     rc = t.arena.ensure(need, s);
     if (rc) return rc;
     Fr *d_w = t.arena.alloc<Fr>(num_vars), *d_wbig = t.arena.alloc<Fr>(num_vars);
@@ -481,14 +490,19 @@ int32_t dg_groth16_prove_msms(uint64_t r1cs_handle, const uint8_t *full_assignme
     for (int k = 0; k < 3; k++) d[k] = t.arena.alloc<Fr>(D);
     tmp = t.arena.alloc<Fr>(D);
     uint8_t *d_res = t.arena.alloc<uint8_t>(288 * (njobs + 1));
-    char *scratch = t.arena.alloc<char>(msm_scratch);
+    char *scratch[2];
+    scratch[0] = t.arena.alloc<char>(msm_scratch);
+    scratch[1] = t.arena.alloc<char>(msm_scratch);
     DG_CUDA(cudaMemcpyAsync(d_w, full_assignment_mont, 32 * num_vars, cudaMemcpyHostToDevice, s));
+    fr_into_bigint_device(d_w, d_wbig, num_vars, s);                            // aux / input assignment
+    DG_CUDA(cudaEventRecord(t.ev_a, s));
+    DG_CUDA(cudaStreamWaitEvent(st[1], t.ev_a, 0));                             // stream B may start on the assignment MSMs
     // a, b, c over the domain: constraint rows, then (a only) the instance variables, zero padding
     const char *blob = (const char *)rr.dev;
     for (int k = 0; k < 3; k++) {
         DG_CUDA(cudaMemsetAsync(d[k] + m.ncons, 0, 32 * (D - m.ncons), s));
         DG_LAUNCH(k_fr_spmv, div_up(m.ncons, 128), 128, 0, s, (const uint32_t *)(blob + m.off_rp[k]), (const uint32_t *)(blob + m.off_col[k]),
-                  (const Fr *)(blob + m.off_co[k]), (uint32_t)m.ncons, d_w, (uint32_t)num_vars, d[k], t.err_flag);
+                  (const Fr *)(blob + m.off_co[k]), (uint32_t)m.ncons, d_w, (uint32_t)num_vars, d[k], t.err_flag + 8);
     }
     DG_CUDA(cudaMemcpyAsync(d[0] + m.ncons, d_w, 32 * m.ninputs, cudaMemcpyDeviceToDevice, s));
     for (int k = 0; k < 3; k++) {
@@ -504,18 +518,39 @@ int32_t dg_groth16_prove_msms(uint64_t r1cs_handle, const uint8_t *full_assignme
     if (rc) return rc;
     if (out_h_mont) DG_CUDA(cudaMemcpyAsync(out_h_mont, d[0], 32 * D, cudaMemcpyDeviceToHost, s));
     fr_into_bigint_device(d[0], d[1], nh, s);                                   // h_assignment
-    fr_into_bigint_device(d_w, d_wbig, num_vars, s);                            // aux / input assignment
+    // static schedule: the h MSM follows the witness map on stream A; every other MSM goes to the stream with less work
+    // queued (cost ~ terms, a G2 term ~3.2 G1 terms; the witness map itself ~ D / 4 terms)
+    double load[2] = {(double)nh + (double)D / 4, 0.0};
+    int where[32];
+    for (size_t j = 0; j < njobs; j++) {
+        double cost = (double)job_count[j] * (jb[j].kind == HandleRec::BASES_G2 ? 3.2 : 1.0);
+        int k = load[1] <= load[0] ? 1 : 0;
+        where[j] = k;
+        load[k] += cost;
+    }
+    where[njobs] = 0;
     uint32_t bad = 0;
-    for (size_t j = 0; j <= njobs; j++) {
+    auto run_job = [&](size_t j) -> int32_t {
+        const int k = where[j];
         const bool g2 = jb[j].kind == HandleRec::BASES_G2;
         const size_t cnt = j < njobs ? job_count[j] : nh;
         const void *sc = j < njobs ? (const void *)(d_wbig + job_offset[j]) : (const void *)d[1];
-        rc = g2 ? msm_run_g2(jb[j].dev, sc, cnt, d_res + 288 * j, scratch, t.err_flag, s, pre_of(jb[j]))
-                : msm_run_g1(jb[j].dev, sc, cnt, d_res + 288 * j, scratch, t.err_flag, s, pre_of(jb[j]));
-        if (rc) return rc;
+        uint32_t *flag = t.err_flag + k;                                     // one flag word per stream
+        int32_t r2 = g2 ? msm_run_g2(jb[j].dev, sc, cnt, d_res + 288 * j, scratch[k], flag, st[k], pre_of(jb[j]))
+                        : msm_run_g1(jb[j].dev, sc, cnt, d_res + 288 * j, scratch[k], flag, st[k], pre_of(jb[j]));
+        if (r2) return r2;
         // msm_run clears the flag when it starts: collect it per MSM
-        DG_CUDA(cudaMemcpyAsync(t.err_flag_host + 1 + (j & 31), t.err_flag, 4, cudaMemcpyDeviceToHost, s));
-    }
+        DG_CUDA(cudaMemcpyAsync(t.err_flag_host + 1 + j, flag, 4, cudaMemcpyDeviceToHost, st[k]));
+        return DG_OK;
+    };
+    // stream B's jobs first (they can start now), then stream A's: h, then the rest
+    for (size_t j = 0; j < njobs; j++)
+        if (where[j] == 1 && (rc = run_job(j))) return rc;
+    if ((rc = run_job(njobs))) return rc;
+    for (size_t j = 0; j < njobs; j++)
+        if (where[j] == 0 && (rc = run_job(j))) return rc;
+    DG_CUDA(cudaEventRecord(t.ev_b, st[1]));
+    DG_CUDA(cudaStreamWaitEvent(s, t.ev_b, 0));
     for (size_t j = 0; j < njobs; j++)
         DG_CUDA(cudaMemcpyAsync(out_jobs_jac + 288 * j, d_res + 288 * j, jb[j].kind == HandleRec::BASES_G2 ? 288 : 144, cudaMemcpyDeviceToHost, s));
     DG_CUDA(cudaMemcpyAsync(out_h_acc_jac, d_res + 288 * njobs, 144, cudaMemcpyDeviceToHost, s));

@@ -666,6 +666,19 @@ EXPORT void ref_qap_h_from_abc(const uint8_t *a_in, const uint8_t *b_in, const u
     memcpy(out_h, a, 32 * n);
     free(a); free(b); free(c);
 }
+/* evaluate_constraint over a whole matrix (legogroth16/src/r1cs_to_qap.rs:13-44, :163-186): CSR times assignment,
+ * Montgomery Fr in and out; rayon-parallel over the rows in the reference, OpenMP here. */
+EXPORT void ref_fr_spmv(const uint32_t *row_ptr, const uint32_t *col, const uint8_t *coeff, size_t rows, const uint8_t *w, uint8_t *out) {
+#pragma omp parallel for schedule(static, 1024)
+    for (size_t i = 0; i < rows; i++) {
+        fr_t acc; memset(&acc, 0, sizeof acc);
+        for (uint32_t k = row_ptr[i]; k < row_ptr[i + 1]; k++) {
+            fr_t c, x, t; memcpy(&c, coeff + 32 * (size_t)k, 32); memcpy(&x, w + 32 * (size_t)col[k], 32);
+            fr_mul(&t, &c, &x); fr_add(&acc, &acc, &t);
+        }
+        memcpy(out + 32 * i, &acc, 32);
+    }
+}
 EXPORT void ref_fr_mul(const uint8_t *a, const uint8_t *b, uint8_t *out) { fr_t x, y, r; memcpy(&x, a, 32); memcpy(&y, b, 32); fr_mul(&r, &x, &y); memcpy(out, &r, 32); }
 
 /* ---- ark-serialize wire format of G1 ("next" row f4; CPU timing baseline and second checker) ----

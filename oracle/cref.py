@@ -233,3 +233,12 @@ def qap_h_from_abc(a, b, c, logn):
     out = np.zeros(32 << logn, np.uint8)
     lib().ref_qap_h_from_abc(xp, yp, zp, C.c_uint32(logn), out.ctypes.data_as(C.c_void_p))
     return out
+
+
+def fr_spmv(row_ptr, col, coeff_mont, w_mont):
+    rp = np.ascontiguousarray(row_ptr, dtype=np.uint32); cl = np.ascontiguousarray(col, dtype=np.uint32)
+    co, cop = _u8(_as_np(coeff_mont)); w, wp = _u8(_as_np(w_mont))
+    rows = rp.size - 1
+    out = np.zeros(32 * rows, np.uint8)
+    lib().ref_fr_spmv(rp.ctypes.data_as(C.c_void_p), cl.ctypes.data_as(C.c_void_p), cop, C.c_size_t(rows), wp, out.ctypes.data_as(C.c_void_p))
+    return out
