@@ -122,7 +122,7 @@ template <class F> static int32_t batch_mul(const uint8_t *points, const uint8_t
     Jac<F> *d_o = t.arena.alloc<Jac<F>>(m);
     DG_CUDA(cudaMemcpyAsync(d_p, points, Sizes<F>::AFF * m, cudaMemcpyHostToDevice, t.stream));
     DG_CUDA(cudaMemcpyAsync(d_s, scalars, 32 * m, cudaMemcpyHostToDevice, t.stream));
-    DG_LAUNCH(k_batch_mul<F>, div_up(m, 128), 128, 0, t.stream, d_p, d_s, (uint32_t)m, d_o);
+    DG_LAUNCH(k_batch_mul<F>, div_up(m, 128), 128, 0, t.stream, d_p, d_s, (uint32_t)m, d_o, ctx().tunable[4].load() == 0 ? 1 : 0);
     DG_CUDA(cudaMemcpyAsync(out_jac, d_o, Sizes<F>::JAC * m, cudaMemcpyDeviceToHost, t.stream));
     DG_CUDA(cudaStreamSynchronize(t.stream));
     return DG_OK;
@@ -151,7 +151,7 @@ static int32_t batch_mul_add_fixed(const uint8_t *points, const uint8_t *sa, uin
     DG_CUDA(cudaMemcpyAsync(d_sa, sa, 32 * m, cudaMemcpyHostToDevice, t.stream));
     DG_CUDA(cudaMemcpyAsync(d_sb, sb, 32 * m, cudaMemcpyHostToDevice, t.stream));
     DG_LAUNCH(k_batch_mul_add_fixed<F>, div_up(m, 128), 128, 0, t.stream, d_p, d_sa, (const Affine<F> *)tb.dev, tb.window,
-              tb.nwin, d_sb, (uint32_t)m, d_o);
+              tb.nwin, d_sb, (uint32_t)m, d_o, ctx().tunable[4].load() == 0 ? 1 : 0);
     normalize_device<F>(d_o, m, d_a, d_prefix, t.stream);
     DG_CUDA(cudaMemcpyAsync(out_affine, d_a, Sizes<F>::AFF * m, cudaMemcpyDeviceToHost, t.stream));
     DG_CUDA(cudaStreamSynchronize(t.stream));

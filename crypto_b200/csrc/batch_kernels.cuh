@@ -10,6 +10,7 @@
 #include "common.cuh"
 #include "ec.cuh"
 #include "fp_inv.cuh"
+#include "glv.cuh"
 
 namespace dg {
 
@@ -81,61 +82,116 @@ template <class F> __device__ __forceinline__ Jac<F> jac_add_z(const Jac<F> &p, 
     if (p_inf) out = {q.x, q.y, q.z};
     return out;
 }
-template <class F> __device__ __forceinline__ Jac<F> scalar_mul(const Affine<F> &p, const uint32_t s[9]) {
-    if (aff_is_inf(p)) return jac_inf<F>();
-    // signed digits, least significant first: d = nibble + carry, d > 8 -> d - 16 and carry (the top nibble of a
-    // 255-bit scalar is <= 7, so the last digit never overflows)
-    uint32_t mag[8];
-    uint64_t neg = 0;
+// signed 4-bit digits of v[0 .. words), least significant first: d = nibble + carry, d > 8 -> d - 16 and carry (callers
+// guarantee the top nibble is <= 7, so the last digit never overflows).  mag nibble = 8 | (|d| - 1), or 0 for d == 0.
+template <int WORDS> __device__ __forceinline__ void recode_w4(const uint32_t *v, uint32_t mag[WORDS], uint64_t &neg) {
+    neg = 0;
     uint32_t carry = 0;
 #pragma unroll
-    for (int w = 0; w < 8; w++) {
+    for (int w = 0; w < WORDS; w++) {
         uint32_t m = 0;
 #pragma unroll
         for (int k = 0; k < 8; k++) {
-            uint32_t d = ((s[w] >> (4 * k)) & 15u) + carry;
+            uint32_t d = ((v[w] >> (4 * k)) & 15u) + carry;
             bool ng = d > 8;
             carry = ng ? 1u : 0u;
             uint32_t a = ng ? 16u - d : d;              // 0 .. 8
-            // magnitude 8 needs a fifth bit: keep magnitude - 1 (0 .. 7) and mark zero digits separately
-            m |= ((a ? a - 1 : 0u) & 7u) << (4 * k) | (a ? 8u : 0u) << (4 * k);
+            m |= (a ? (8u | (a - 1)) : 0u) << (4 * k);
             neg |= (uint64_t)(ng ? 1u : 0u) << (8 * w + k);
         }
         mag[w] = m;
     }
-    JacZ<F> tbl[8];
-    {
-        Jac<F> p1 = {p.x, p.y, fone<F>()};
-        Jac<F> p2 = jac_dbl(p1), p3 = jac_madd(p2, p), p4 = jac_dbl(p2);
-        Jac<F> p5 = jac_madd(p4, p), p6 = jac_dbl(p3), p7 = jac_madd(p6, p), p8 = jac_dbl(p4);
-        tbl[0] = {p.x, p.y, fone<F>(), fone<F>(), fone<F>()};
-        tbl[1] = jacz_of(p2); tbl[2] = jacz_of(p3); tbl[3] = jacz_of(p4);
-        tbl[4] = jacz_of(p5); tbl[5] = jacz_of(p6); tbl[6] = jacz_of(p7); tbl[7] = jacz_of(p8);
+}
+template <class F> __device__ __forceinline__ void scalar_mul_table(const Affine<F> &p, JacZ<F> tbl[8]) {
+    Jac<F> p1 = {p.x, p.y, fone<F>()};
+    Jac<F> p2 = jac_dbl(p1), p3 = jac_madd(p2, p), p4 = jac_dbl(p2);
+    Jac<F> p5 = jac_madd(p4, p), p6 = jac_dbl(p3), p7 = jac_madd(p6, p), p8 = jac_dbl(p4);
+    tbl[0] = {p.x, p.y, fone<F>(), fone<F>(), fone<F>()};
+    tbl[1] = jacz_of(p2); tbl[2] = jacz_of(p3); tbl[3] = jacz_of(p4);
+    tbl[4] = jacz_of(p5); tbl[5] = jacz_of(p6); tbl[6] = jacz_of(p7); tbl[7] = jacz_of(p8);
+}
+// out-of-line group operations: one copy of each in the kernel instead of one per call site
+template <class F> static __device__ __noinline__ Jac<F> jac_dbl_ni(const Jac<F> &p) { return jac_dbl(p); }
+template <class F> static __device__ __noinline__ Jac<F> jac_add_z_ni(const Jac<F> &p, const JacZ<F> &q) { return jac_add_z(p, q); }
+template <class F> static __device__ __noinline__ void scalar_mul_table_ni(const Affine<F> &p, JacZ<F> *tbl) { scalar_mul_table(p, tbl); }
+
+// [s] P for s < 2^255, signed 4-bit windows, uniform instruction stream.
+//   canonical scalar (< r), P in the prime-order subgroup -- what every reference call site passes
+//   (mul_bigint(fr.into_bigint()) on deserialised, hence validated, points) -- and glv != 0:
+//       GLV split s = +-k1 - k2 lambda, the two 127-bit halves share ONE chain of 128 doublings (Shamir's trick), phi is
+//       applied to the table entry on the fly (one multiplication by beta): 128 dbl + 64 add;
+//   otherwise (s >= r is not a field element but a legal BigInt): the plain 64-digit chain, 256 dbl + 64 add.
+template <class F> static __device__ __noinline__ Jac<F> scalar_mul_w4(const Affine<F> &p, const uint32_t s_in[9], int glv) {
+    if (aff_is_inf(p)) return jac_inf<F>();
+    uint32_t mag[2][8];
+    uint64_t ng[2] = {0, 0};
+    bool sgn[2] = {false, false};
+    int ndig = 64, halves = 1;
+    bool split = false;
+    if (glv) {
+        constexpr uint32_t RM[8] = {DG_R0, DG_R1, DG_R2, DG_R3, DG_R4, DG_R5, DG_R6, DG_R7};
+        uint32_t s[8], t[8], borrow = 0;
+#pragma unroll
+        for (int k = 0; k < 8; k++) {                      // t = r - s
+            uint64_t d = (uint64_t)RM[k] - s_in[k] - borrow;
+            t[k] = (uint32_t)d;
+            borrow = (uint32_t)(d >> 63);
+        }
+        bool t_zero = true, decided = false, t_less = false;
+#pragma unroll
+        for (int k = 7; k >= 0; k--) {
+            t_zero &= t[k] == 0;
+            if (!decided && t[k] != s_in[k]) { t_less = t[k] < s_in[k]; decided = true; }
+        }
+        if (!borrow && !t_zero) {                          // s < r
+            const bool flip = t_less;
+#pragma unroll
+            for (int k = 0; k < 8; k++) s[k] = flip ? t[k] : s_in[k];
+            uint32_t k1[4], k2[4];
+            bool neg1;
+            glv_split(s, k1, neg1, k2);
+            recode_w4<4>(k1, mag[0], ng[0]);
+            recode_w4<4>(k2, mag[1], ng[1]);
+            sgn[0] = flip != neg1;                         // [s] P = sigma ( +-[k1] P - [k2] phi(P) )
+            sgn[1] = !flip;
+            ndig = 32; halves = 2;
+            split = true;
+        }
     }
+    if (!split) recode_w4<8>(s_in, mag[0], ng[0]);
+    JacZ<F> tbl[8];
+    scalar_mul_table_ni(p, tbl);
+    Fp beta;
+#pragma unroll
+    for (int k = 0; k < 12; k++) beta.l[k] = sizeof(F) > 48 ? DGC_GLV_BETA_G2[k] : DGC_GLV_BETA_G1[k];
     Jac<F> acc = jac_inf<F>();
 #pragma unroll 1
-    for (int dig = 63; dig >= 0; dig--) {
+    for (int dig = ndig - 1; dig >= 0; dig--) {
 #pragma unroll 1
-        for (int k = 0; k < 4; k++) acc = jac_dbl(acc);
-        uint32_t nib = (mag[dig >> 3] >> (4 * (dig & 7))) & 15u;
-        bool nz = (nib & 8u) != 0, ng = (neg >> dig) & 1u;
-        JacZ<F> q = tbl[nib & 7u];
-        q.y = fcneg(q.y, ng);
-        Jac<F> sum = jac_add_z(acc, q);
-        acc.x = fsel(nz, sum.x, acc.x); acc.y = fsel(nz, sum.y, acc.y); acc.z = fsel(nz, sum.z, acc.z);
+        for (int k = 0; k < 4; k++) acc = jac_dbl_ni(acc);
+#pragma unroll 1
+        for (int half = 0; half < halves; half++) {
+            uint32_t nib = (mag[half][dig >> 3] >> (4 * (dig & 7))) & 15u;
+            bool nz = (nib & 8u) != 0, neg = (((ng[half] >> dig) & 1u) != 0) != sgn[half];
+            JacZ<F> q = tbl[nib & 7u];
+            if (half) q.x = glv_mul_beta(q.x, beta);        // phi((X, Y, Z)) = (beta X, Y, Z)
+            q.y = fcneg(q.y, neg);
+            Jac<F> sum = jac_add_z_ni(acc, q);
+            acc.x = fsel(nz, sum.x, acc.x); acc.y = fsel(nz, sum.y, acc.y); acc.z = fsel(nz, sum.z, acc.z);
+        }
     }
     return acc;
 }
 
 template <class F>
 __global__ void __launch_bounds__(128) k_batch_mul(const Affine<F> *__restrict__ points, const uint8_t *__restrict__ scalars,
-                                                   uint32_t m, Jac<F> *__restrict__ out) {
+                                                   uint32_t m, Jac<F> *__restrict__ out, int glv) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= m) return;
     uint32_t s[9];
     load_scalar(scalars, i, s);
     Affine<F> p = aff_load<F>(&points[i]);
-    jac_store(&out[i], scalar_mul(p, s));
+    jac_store(&out[i], scalar_mul_w4(p, s, glv));
 }
 
 // ---- fixed-base tables -------------------------------------------------------------------------
@@ -195,13 +251,13 @@ __global__ void __launch_bounds__(128) k_fixed_mul_many(const Affine<F> *__restr
 template <class F>
 __global__ void __launch_bounds__(128) k_batch_mul_add_fixed(const Affine<F> *__restrict__ points, const uint8_t *__restrict__ sa,
                                                              const Affine<F> *__restrict__ table, int window, int outerc,
-                                                             const uint8_t *__restrict__ sb, uint32_t m, Jac<F> *__restrict__ out) {
+                                                             const uint8_t *__restrict__ sb, uint32_t m, Jac<F> *__restrict__ out, int glv) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= m) return;
     uint32_t s[9];
     load_scalar(sa, i, s);
     Affine<F> p = aff_load<F>(&points[i]);
-    XYZZ<F> acc = jac_to_xyzz(scalar_mul(p, s));
+    XYZZ<F> acc = jac_to_xyzz(scalar_mul_w4(p, s, glv));
     load_scalar(sb, i, s);
     for (int k = 0; k < outerc; k++) {
         uint32_t idx = scalar_bits(s, k * window, window);

@@ -77,3 +77,27 @@ def test_glv_with_identity_equal_and_opposite_bases(dg, cref):
     assert h.affine_g1(dg.msm(bytes(b), ss)) == h.affine_g1(cref.msm_g1(np.frombuffer(bytes(b), dtype=np.uint8), ss))
     same = np.frombuffer(bytes(b[96:192]) * n, dtype=np.uint8)       # every base equal: one hot bucket per window
     assert h.affine_g1(dg.msm(same, ss)) == h.affine_g1(cref.msm_g1(same, ss))
+
+
+@pytest.mark.parametrize('g2', [False, True])
+def test_batch_mul_glv_edge_scalars_and_non_field_bigints(dg, cref, g2):
+    """dg_batch_mul: canonical scalars take the GLV path, integers >= r (legal BigInts for mul_bigint) the generic
+    64-digit path; both equal the oracle's double-and-add, identity points included."""
+    big = [R, R + 1, (1 << 255) - 1, (1 << 255) - 19, R + msm.GLV_X2, 2 * R - 1]
+    scal = [e % (1 << 255) for e in EDGE] + big + h.ints_of(h.rand_scalars(40, 91))
+    n = len(scal)
+    pts, _ = (h.g2_bases if g2 else h.g1_bases)(n, 92)
+    rec = 192 if g2 else 96
+    b = bytearray(bytes(pts))
+    b[rec * 3:rec * 4] = bytes(rec)                       # one identity point
+    sb = np.frombuffer(b''.join(int(s).to_bytes(32, 'little') for s in scal), dtype=np.uint8)
+    exp = (cref.batch_mul_g2 if g2 else cref.batch_mul_g1)(np.frombuffer(bytes(b), dtype=np.uint8), sb)
+    aff = h.affine_g2 if g2 else h.affine_g1
+    try:
+        _glv(dg, True)
+        got = dg.batch_mul(bytes(b), sb, g2=g2)
+        _glv(dg, False)
+        got_plain = dg.batch_mul(bytes(b), sb, g2=g2)
+    finally:
+        _glv(dg, True)
+    assert aff(got) == aff(exp) == aff(got_plain)
