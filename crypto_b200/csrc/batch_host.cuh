@@ -128,30 +128,47 @@ template <class F> static int32_t batch_mul(const uint8_t *points, const uint8_t
     return DG_OK;
 }
 
+// v_affine != nullptr: V given directly, no window table (always the joint form)
 template <class F>
 static int32_t batch_mul_add_fixed(const uint8_t *points, const uint8_t *sa, uint64_t handle, const uint8_t *sb, size_t m,
-                                   uint8_t *out_affine) {
+                                   uint8_t *out_affine, const uint8_t *v_affine = nullptr) {
     int32_t rc = check_init();
     if (rc) return rc;
     if (m && (!points || !sa || !sb || !out_affine)) return fail(DG_ERR_BAD_ARG, "batch_mul_add_fixed: null pointer");
     HandleRec tb;
-    rc = lookup_table<F>(handle, tb);
-    if (rc) return rc;
+    if (!v_affine) {
+        rc = lookup_table<F>(handle, tb);
+        if (rc) return rc;
+    }
     if (m == 0) return DG_OK;
     ThreadState &t = tls();
     rc = t.arena.ensure(2 * Arena::pad(Sizes<F>::AFF * m) + 2 * Arena::pad(32 * m) + Arena::pad(Sizes<F>::JAC * m) +
-                            Arena::pad(sizeof(F) * m), t.stream);
+                            Arena::pad(sizeof(F) * m) + Arena::pad(sizeof(JacZ<F>) * 8) + Arena::pad(Sizes<F>::AFF), t.stream);
     if (rc) return rc;
+    Affine<F> *d_v = t.arena.alloc<Affine<F>>(1);
+    if (v_affine) DG_CUDA(cudaMemcpyAsync(d_v, v_affine, Sizes<F>::AFF, cudaMemcpyHostToDevice, t.stream));
     Affine<F> *d_p = t.arena.alloc<Affine<F>>(m);
     Affine<F> *d_a = t.arena.alloc<Affine<F>>(m);
     uint8_t *d_sa = t.arena.alloc<uint8_t>(32 * m), *d_sb = t.arena.alloc<uint8_t>(32 * m);
     Jac<F> *d_o = t.arena.alloc<Jac<F>>(m);
     F *d_prefix = t.arena.alloc<F>(m);
+    JacZ<F> *d_vtbl = t.arena.alloc<JacZ<F>>(8);
     DG_CUDA(cudaMemcpyAsync(d_p, points, Sizes<F>::AFF * m, cudaMemcpyHostToDevice, t.stream));
     DG_CUDA(cudaMemcpyAsync(d_sa, sa, 32 * m, cudaMemcpyHostToDevice, t.stream));
     DG_CUDA(cudaMemcpyAsync(d_sb, sb, 32 * m, cudaMemcpyHostToDevice, t.stream));
-    DG_LAUNCH(k_batch_mul_add_fixed<F>, div_up(m, 128), 128, 0, t.stream, d_p, d_sa, (const Affine<F> *)tb.dev, tb.window,
-              tb.nwin, d_sb, (uint32_t)m, d_o, ctx().tunable[4].load() == 0 ? 1 : 0);
+    const int glv = ctx().tunable[4].load() == 0 ? 1 : 0;
+    // Below ~2^16 elements the call is latency-bound (one thread per element cannot fill the GPU): both products on one
+    // doubling chain.  Larger batches are throughput-bound and the window table's 29 mixed additions per element are
+    // cheaper than 64 more full additions.  tunable 5: 1 forces the joint form, 2 the table form.
+    const int force = ctx().tunable[5].load();
+    const bool joint = v_affine || force == 1 || (force != 2 && m < 65536);
+    if (joint) {
+        DG_LAUNCH(k_w4_table<F>, 1, 32, 0, t.stream, v_affine ? d_v : (const Affine<F> *)tb.dev + 1, d_vtbl);     // table[0][1] = V
+        DG_LAUNCH(k_batch_mul_add_joint<F>, div_up(m, 128), 128, 0, t.stream, d_p, d_sa, d_vtbl, d_sb, (uint32_t)m, d_o, glv);
+    } else {
+        DG_LAUNCH(k_batch_mul_add_fixed<F>, div_up(m, 128), 128, 0, t.stream, d_p, d_sa, (const Affine<F> *)tb.dev, tb.window,
+                  tb.nwin, d_sb, (uint32_t)m, d_o, glv);
+    }
     normalize_device<F>(d_o, m, d_a, d_prefix, t.stream);
     DG_CUDA(cudaMemcpyAsync(out_affine, d_a, Sizes<F>::AFF * m, cudaMemcpyDeviceToHost, t.stream));
     DG_CUDA(cudaStreamSynchronize(t.stream));

@@ -82,9 +82,9 @@ template <class F> __device__ __forceinline__ Jac<F> jac_add_z(const Jac<F> &p, 
     if (p_inf) out = {q.x, q.y, q.z};
     return out;
 }
-// signed 4-bit digits of v[0 .. words), least significant first: d = nibble + carry, d > 8 -> d - 16 and carry (callers
-// guarantee the top nibble is <= 7, so the last digit never overflows).  mag nibble = 8 | (|d| - 1), or 0 for d == 0.
-template <int WORDS> __device__ __forceinline__ void recode_w4(const uint32_t *v, uint32_t mag[WORDS], uint64_t &neg) {
+// signed 4-bit digits of v[0 .. words), least significant first: d = nibble + carry, d > 8 -> d - 16 and carry; the
+// carry out of the top nibble is returned (always 0 when that nibble is <= 7).  mag nibble = 8 | (|d| - 1), or 0 for d == 0.
+template <int WORDS> __device__ __forceinline__ uint32_t recode_w4(const uint32_t *v, uint32_t mag[WORDS], uint64_t &neg) {
     neg = 0;
     uint32_t carry = 0;
 #pragma unroll
@@ -101,6 +101,7 @@ template <int WORDS> __device__ __forceinline__ void recode_w4(const uint32_t *v
         }
         mag[w] = m;
     }
+    return carry;                                       // a 65th digit (0 or 1) for 256-bit integers whose top nibble exceeds 7
 }
 template <class F> __device__ __forceinline__ void scalar_mul_table(const Affine<F> &p, JacZ<F> tbl[8]) {
     Jac<F> p1 = {p.x, p.y, fone<F>()};
@@ -115,52 +116,67 @@ template <class F> static __device__ __noinline__ Jac<F> jac_dbl_ni(const Jac<F>
 template <class F> static __device__ __noinline__ Jac<F> jac_add_z_ni(const Jac<F> &p, const JacZ<F> &q) { return jac_add_z(p, q); }
 template <class F> static __device__ __noinline__ void scalar_mul_table_ni(const Affine<F> &p, JacZ<F> *tbl) { scalar_mul_table(p, tbl); }
 
-// [s] P for s < 2^255, signed 4-bit windows, uniform instruction stream.
-//   canonical scalar (< r), P in the prime-order subgroup -- what every reference call site passes
+// [s] P (+ [s2] V) for 256-bit integers, signed 4-bit windows, uniform instruction stream.
+//   canonical scalars (< r), points in the prime-order subgroup -- what every reference call site passes
 //   (mul_bigint(fr.into_bigint()) on deserialised, hence validated, points) -- and glv != 0:
-//       GLV split s = +-k1 - k2 lambda, the two 127-bit halves share ONE chain of 128 doublings (Shamir's trick), phi is
-//       applied to the table entry on the fly (one multiplication by beta): 128 dbl + 64 add;
-//   otherwise (s >= r is not a field element but a legal BigInt): the plain 64-digit chain, 256 dbl + 64 add.
-template <class F> static __device__ __noinline__ Jac<F> scalar_mul_w4(const Affine<F> &p, const uint32_t s_in[9], int glv) {
-    if (aff_is_inf(p)) return jac_inf<F>();
-    uint32_t mag[2][8];
-    uint64_t ng[2] = {0, 0};
-    bool sgn[2] = {false, false};
-    int ndig = 64, halves = 1;
+//       GLV split s = +-k1 - k2 lambda; the 127-bit halves of every scalar share ONE chain of 128 doublings (Shamir's
+//       trick), phi is applied to the table entry on the fly (one multiplication by beta): 128 dbl + 64 add per scalar;
+//   otherwise (s >= r is not a field element but a legal BigInt): the plain 65-digit chain, 256 dbl + 64 add.
+// vtbl != nullptr adds [s2] V with V's eight multiples read from global memory (k_w4_table): the fused accumulator
+// witness update d * C_i + v * V (vb_accumulator/src/witness.rs:269-284) on one doubling chain.
+template <class F> struct W4Digits { uint32_t mag[4][8]; uint64_t ng[4]; bool sgn[4]; uint32_t top[4]; };
+template <class F> __device__ __forceinline__ bool w4_split(const uint32_t s_in[9], uint32_t *mag1, uint64_t &ng1, bool &sgn1, uint32_t *mag2,
+                                                           uint64_t &ng2, bool &sgn2) {
+    constexpr uint32_t RM[8] = {DG_R0, DG_R1, DG_R2, DG_R3, DG_R4, DG_R5, DG_R6, DG_R7};
+    uint32_t s[8], t[8], borrow = 0;
+#pragma unroll
+    for (int k = 0; k < 8; k++) {                      // t = r - s
+        uint64_t d = (uint64_t)RM[k] - s_in[k] - borrow;
+        t[k] = (uint32_t)d;
+        borrow = (uint32_t)(d >> 63);
+    }
+    bool t_zero = true, decided = false, t_less = false;
+#pragma unroll
+    for (int k = 7; k >= 0; k--) {
+        t_zero &= t[k] == 0;
+        if (!decided && t[k] != s_in[k]) { t_less = t[k] < s_in[k]; decided = true; }
+    }
+    if (borrow || t_zero) return false;                // s >= r
+    const bool flip = t_less;
+#pragma unroll
+    for (int k = 0; k < 8; k++) s[k] = flip ? t[k] : s_in[k];
+    uint32_t k1[4], k2[4];
+    bool neg1;
+    glv_split(s, k1, neg1, k2);
+    recode_w4<4>(k1, mag1, ng1);
+    recode_w4<4>(k2, mag2, ng2);
+    sgn1 = flip != neg1;                               // [s] P = sigma ( +-[k1] P - [k2] phi(P) )
+    sgn2 = !flip;
+    return true;
+}
+template <class F>
+static __device__ __noinline__ Jac<F> scalar_mul_w4(const Affine<F> &p, const uint32_t s_in[9], int glv, const JacZ<F> *vtbl = nullptr,
+                                                    const uint32_t *s2_in = nullptr) {
+    W4Digits<F> dg_;
+    int ndig = 65, halves = 1;
     bool split = false;
+    const bool p_inf = aff_is_inf(p);
+    if (vtbl && fis_zero(vtbl[0].z)) vtbl = nullptr;       // V is the identity (k_w4_table marks it with Z = 0)
     if (glv) {
-        constexpr uint32_t RM[8] = {DG_R0, DG_R1, DG_R2, DG_R3, DG_R4, DG_R5, DG_R6, DG_R7};
-        uint32_t s[8], t[8], borrow = 0;
-#pragma unroll
-        for (int k = 0; k < 8; k++) {                      // t = r - s
-            uint64_t d = (uint64_t)RM[k] - s_in[k] - borrow;
-            t[k] = (uint32_t)d;
-            borrow = (uint32_t)(d >> 63);
-        }
-        bool t_zero = true, decided = false, t_less = false;
-#pragma unroll
-        for (int k = 7; k >= 0; k--) {
-            t_zero &= t[k] == 0;
-            if (!decided && t[k] != s_in[k]) { t_less = t[k] < s_in[k]; decided = true; }
-        }
-        if (!borrow && !t_zero) {                          // s < r
-            const bool flip = t_less;
-#pragma unroll
-            for (int k = 0; k < 8; k++) s[k] = flip ? t[k] : s_in[k];
-            uint32_t k1[4], k2[4];
-            bool neg1;
-            glv_split(s, k1, neg1, k2);
-            recode_w4<4>(k1, mag[0], ng[0]);
-            recode_w4<4>(k2, mag[1], ng[1]);
-            sgn[0] = flip != neg1;                         // [s] P = sigma ( +-[k1] P - [k2] phi(P) )
-            sgn[1] = !flip;
-            ndig = 32; halves = 2;
-            split = true;
+        split = w4_split<F>(s_in, dg_.mag[0], dg_.ng[0], dg_.sgn[0], dg_.mag[1], dg_.ng[1], dg_.sgn[1]);
+        if (split && vtbl) split = w4_split<F>(s2_in, dg_.mag[2], dg_.ng[2], dg_.sgn[2], dg_.mag[3], dg_.ng[3], dg_.sgn[3]);
+        if (split) { ndig = 32; halves = vtbl ? 4 : 2; }
+    }
+    if (!split) {
+        dg_.top[0] = recode_w4<8>(s_in, dg_.mag[0], dg_.ng[0]);
+        dg_.sgn[0] = false;
+        if (vtbl) {                                        // second scalar on the same 65-digit chain: halves 0 (P) and 2 (V)
+            dg_.top[2] = recode_w4<8>(s2_in, dg_.mag[2], dg_.ng[2]);
+            dg_.sgn[2] = false;
         }
     }
-    if (!split) recode_w4<8>(s_in, mag[0], ng[0]);
     JacZ<F> tbl[8];
-    scalar_mul_table_ni(p, tbl);
+    if (!p_inf) scalar_mul_table_ni(p, tbl);
     Fp beta;
 #pragma unroll
     for (int k = 0; k < 12; k++) beta.l[k] = sizeof(F) > 48 ? DGC_GLV_BETA_G2[k] : DGC_GLV_BETA_G1[k];
@@ -170,17 +186,33 @@ template <class F> static __device__ __noinline__ Jac<F> scalar_mul_w4(const Aff
 #pragma unroll 1
         for (int k = 0; k < 4; k++) acc = jac_dbl_ni(acc);
 #pragma unroll 1
-        for (int half = 0; half < halves; half++) {
-            uint32_t nib = (mag[half][dig >> 3] >> (4 * (dig & 7))) & 15u;
-            bool nz = (nib & 8u) != 0, neg = (((ng[half] >> dig) & 1u) != 0) != sgn[half];
-            JacZ<F> q = tbl[nib & 7u];
-            if (half) q.x = glv_mul_beta(q.x, beta);        // phi((X, Y, Z)) = (beta X, Y, Z)
+        for (int half = 0; half < 4; half++) {
+            const bool use = split ? half < halves : (half == 0 || (half == 2 && vtbl != nullptr));
+            if (!use) continue;                                                  // uniform across the warp's split / unsplit lanes only
+            const bool on_v = half >= 2;
+            if (!on_v && p_inf) continue;
+            uint32_t nib = dig < 64 ? (dg_.mag[half][dig >> 3] >> (4 * (dig & 7))) & 15u : (dg_.top[half] ? 8u : 0u);
+            bool nz = (nib & 8u) != 0, neg = dig < 64 && ((((dg_.ng[half] >> dig) & 1u) != 0) != dg_.sgn[half]);
+            JacZ<F> q = on_v ? vtbl[nib & 7u] : tbl[nib & 7u];
+            if (split && (half & 1)) q.x = glv_mul_beta(q.x, beta);             // phi((X, Y, Z)) = (beta X, Y, Z)
             q.y = fcneg(q.y, neg);
             Jac<F> sum = jac_add_z_ni(acc, q);
             acc.x = fsel(nz, sum.x, acc.x); acc.y = fsel(nz, sum.y, acc.y); acc.z = fsel(nz, sum.z, acc.z);
         }
     }
     return acc;
+}
+// the eight multiples of V with their Z^2, Z^3 (table of the shared point of the fused update), one thread
+template <class F> __global__ void k_w4_table(const Affine<F> *v, JacZ<F> *out) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    Affine<F> p = aff_load<F>(v);
+    JacZ<F> tbl[8];
+    if (aff_is_inf(p)) {
+        for (int j = 0; j < 8; j++) tbl[j] = {fone<F>(), fone<F>(), fzero<F>(), fzero<F>(), fzero<F>()};
+    } else {
+        scalar_mul_table(p, tbl);
+    }
+    for (int j = 0; j < 8; j++) out[j] = tbl[j];
 }
 
 template <class F>
@@ -265,6 +297,22 @@ __global__ void __launch_bounds__(128) k_batch_mul_add_fixed(const Affine<F> *__
         acc = xyzz_madd(acc, q);
     }
     jac_store(&out[i], xyzz_to_jac(acc));
+}
+
+// out[i] = [a_i] P_i + [b_i] V on ONE doubling chain per element (no window table): the latency-optimal form of the fused
+// update for batches that cannot fill the GPU (10^4 witnesses = 79 CTAs), where the 255 sequential doublings of building
+// V's window table would cost more than the table saves.
+template <class F>
+__global__ void __launch_bounds__(128) k_batch_mul_add_joint(const Affine<F> *__restrict__ points, const uint8_t *__restrict__ sa,
+                                                             const JacZ<F> *__restrict__ vtbl, const uint8_t *__restrict__ sb, uint32_t m,
+                                                             Jac<F> *__restrict__ out, int glv) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= m) return;
+    uint32_t s[9], s2[9];
+    load_scalar(sa, i, s);
+    load_scalar(sb, i, s2);
+    Affine<F> p = aff_load<F>(&points[i]);
+    jac_store(&out[i], scalar_mul_w4(p, s, glv, vtbl, s2));
 }
 
 // ---- normalize_batch ---------------------------------------------------------------------------

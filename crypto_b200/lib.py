@@ -27,7 +27,7 @@ EXPORTS = [
     'dg_fixed_base_table_download', 'dg_fixed_base_table_free',
     'dg_fixed_base_mul_many_g1', 'dg_fixed_base_mul_many_g2',
     'dg_fixed_base_mul_many_normalized_g1', 'dg_fixed_base_mul_many_normalized_g2',
-    'dg_batch_mul_g1', 'dg_batch_mul_g2', 'dg_batch_mul_add_fixed_g1',
+    'dg_batch_mul_g1', 'dg_batch_mul_g2', 'dg_batch_mul_add_fixed_g1', 'dg_batch_mul_add_same_g1',
     'dg_normalize_batch_g1', 'dg_normalize_batch_g2',
     'dg_multi_miller_loop', 'dg_final_exponentiation', 'dg_multi_pairing', 'dg_multi_pairing_is_one', 'dg_multi_pairing_batch',
     'dg_gt_pow', 'dg_fp12_mul',
@@ -340,6 +340,18 @@ def batch_mul_add_fixed_g1(points, scalars_a, table, scalars_b):
         raise ValueError('batch_mul_add_fixed_g1: points, scalars_a and scalars_b must describe the same number of elements')
     o, op = _out(G1_AFF * m)
     _check(lib.dg_batch_mul_add_fixed_g1(pp, ap, C.c_uint64(table.handle), bp, C.c_size_t(m), op))
+    return o[:G1_AFF * m]
+
+
+def batch_mul_add_same_g1(points, scalars_a, v_affine, scalars_b):
+    """out[i] = normalize([a_i] P_i + [b_i] V) with V given directly (no window table)."""
+    lib = init()
+    p, pp = _in(points); a, ap = _in(scalars_a); b, bp = _in(scalars_b); v, vp = _in(v_affine)
+    m = a.size // SCALAR
+    if a.size % SCALAR or b.size != a.size or p.size != G1_AFF * m or v.size != G1_AFF:
+        raise ValueError('batch_mul_add_same_g1: points, scalars_a and scalars_b must describe the same number of elements')
+    o, op = _out(G1_AFF * m)
+    _check(lib.dg_batch_mul_add_same_g1(pp, ap, vp, bp, C.c_size_t(m), op))
     return o[:G1_AFF * m]
 
 

@@ -423,12 +423,17 @@ def compute_update_using_secret_key_after_batch_updates(additions, removals, ele
         d_D_inv = pow(Poly_d.eval_direct(removals, y), -1, R_MODULUS)
         d_factors.append(Poly_d.eval_direct(additions, y) * d_D_inv % R_MODULUS)
         v_factors.append(v * d_D_inv % R_MODULUS)
-    table = msm_mod.WindowTable.new(m, old_accumulator)
-    try:
-        out = lib.batch_mul_add_fixed_g1(np.frombuffer(bytes(old_witnesses), dtype=np.uint8), gp.fr_to_bytes(d_factors), table._t,
-                                         gp.fr_to_bytes(v_factors))
-    finally:
-        table.free()
+    wits = np.frombuffer(bytes(old_witnesses), dtype=np.uint8)
+    if m < 65536:
+        # at the reference's batch sizes the device shares one doubling chain between d * C_i and v * V instead of building
+        # WindowTable::new(m, V) first (dg_batch_mul_add_same_g1)
+        out = lib.batch_mul_add_same_g1(wits, gp.fr_to_bytes(d_factors), old_accumulator, gp.fr_to_bytes(v_factors))
+    else:
+        table = msm_mod.WindowTable.new(m, old_accumulator)
+        try:
+            out = lib.batch_mul_add_fixed_g1(wits, gp.fr_to_bytes(d_factors), table._t, gp.fr_to_bytes(v_factors))
+        finally:
+            table.free()
     return d_factors, bytes(out)
 
 

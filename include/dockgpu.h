@@ -155,13 +155,20 @@ int32_t dg_fixed_base_mul_many_normalized_g2(uint64_t table_handle, const uint8_
 
 /* ---- independent scalar multiplications ----------------------------------------------------
  * AffineRepr::mul_bigint inside cfg_iter! maps (vb_accumulator/src/witness.rs:190,229,278;
- * utils/src/randomized_pairing_check.rs:126,153,157): out[i] = [s_i] P_i, Jacobian. */
+ * utils/src/randomized_pairing_check.rs:126,153,157): out[i] = [s_i] P_i, Jacobian.  Scalars are 256-bit integers
+ * (BigInt<4>, not necessarily < r).  Canonical scalars use the GLV endomorphism, which like the MSM assumes points of
+ * the prime-order subgroup (every point the reference passes: deserialisation validates). */
 int32_t dg_batch_mul_g1(const uint8_t *points_affine, const uint8_t *scalars, size_t m, uint8_t *out_jac);
 int32_t dg_batch_mul_g2(const uint8_t *points_affine, const uint8_t *scalars, size_t m, uint8_t *out_jac);
 /* Fused accumulator witness update (vb_accumulator/src/witness.rs:269-284):
  * out[i] = normalize( [a_i] P_i + [b_i] V ), V given by its window table.  out: m affine. */
 int32_t dg_batch_mul_add_fixed_g1(const uint8_t *points_affine, const uint8_t *scalars_a, uint64_t table_handle,
                                   const uint8_t *scalars_b, size_t m, uint8_t *out_affine);
+/* Same result with V given as one affine point instead of its window table: for the batch sizes of the reference's
+ * workloads (10^4 witnesses) building WindowTable::new(m, V) costs more than it saves on a GPU (255 sequential
+ * doublings), so both products of an element share one doubling chain instead. */
+int32_t dg_batch_mul_add_same_g1(const uint8_t *points_affine, const uint8_t *scalars_a, const uint8_t *v_affine,
+                                 const uint8_t *scalars_b, size_t m, uint8_t *out_affine);
 
 /* ---- CurveGroup::normalize_batch ------------------------------------------------------------
  * (vb_accumulator/src/witness.rs:193,232,284; batch_utils.rs:506,524,633,651). */

@@ -236,9 +236,32 @@ def test_fused_witness_update(dg, cref):
     pts, _ = h.g1_bases(m, 90)
     v, _ = h.g1_bases(1, 91)
     sa, sb = h.rand_scalars(m, 92), h.rand_scalars(m, 93)
+    sa, sb = np.array(sa), np.array(sb)
+    R_ = o.R
+    # corner cases: zero scalars, a = b = r - 1, an integer >= r (generic chain), an identity witness, C_i = +-V
+    sa[:32] = 0
+    sb[32:64] = 0
+    sa[64:96] = np.frombuffer((R_ - 1).to_bytes(32, 'little'), dtype=np.uint8)
+    sb[96:128] = np.frombuffer((R_ + 5).to_bytes(32, 'little'), dtype=np.uint8)
+    pts = np.array(pts)
+    pts[96 * 4:96 * 5] = 0
+    pts[96 * 5:96 * 6] = np.frombuffer(bytes(v), dtype=np.uint8)
+    pts[96 * 6:96 * 7] = np.frombuffer(h.neg_g1(bytes(v)), dtype=np.uint8)
     t = dg.FixedBaseTable(v, m)
-    out = dg.batch_mul_add_fixed_g1(pts, sa, t, sb)
+    outs = []
+    try:
+        for force in (1, 2):                       # joint doubling chain / window table
+            dg.dbg_set_tunable(5, force)
+            outs.append(bytes(dg.batch_mul_add_fixed_g1(pts, sa, t, sb)))
+    finally:
+        dg.dbg_set_tunable(5, 0)
     t.free()
+    outs.append(bytes(dg.batch_mul_add_same_g1(pts, sa, v, sb)))
+    assert outs[0] == outs[1] == outs[2]
+    out = outs[0]
+    # V = identity: only the a_i * C_i terms remain
+    only_a = bytes(dg.batch_mul_add_same_g1(pts, sa, bytes(96), sb))
+    assert only_a == bytes(dg.normalize_batch(dg.batch_mul(pts, sa)))
     left = cref.batch_mul_g1(pts, sa)
     right, _, _ = cref.fixed_base_mul_many_g1(v, m, sb)
     exp = b''
