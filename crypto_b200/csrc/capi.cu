@@ -24,6 +24,8 @@ ThreadState::~ThreadState() {
         if (stream2) cudaStreamDestroy(stream2);
         if (ev_a) cudaEventDestroy(ev_a);
         if (ev_b) cudaEventDestroy(ev_b);
+        for (int k = 0; k < 4; k++)
+            if (stage_ev[k]) cudaEventDestroy(stage_ev[k]);
         cudaStreamDestroy(stream);
     }
 }
@@ -217,7 +219,32 @@ static int32_t msm_host(uint64_t handle, const uint8_t *bases, const uint8_t *sc
     uint8_t *d_scalars = t.arena.alloc<uint8_t>(32 * n);
     uint8_t *d_out = t.arena.alloc<uint8_t>(JAC);
     if (out_keep_dev) d_out = (uint8_t *)out_keep_dev;
-    if (n) DG_CUDA(cudaMemcpyAsync(d_scalars, scalars, 32 * n, cudaMemcpyHostToDevice, t.stream));
+    // Large inputs arrive in four chunks on a second stream so the PCIe transfer overlaps the histogram pass (pinned
+    // host memory makes the copies truly asynchronous; pageable memory still works, without the overlap).
+    MsmStage stage = {1, {}, {0, n, n, n, n}};
+    const bool chunked = n >= (1u << 18) && !mont_scalars;
+    if (chunked) {
+        if (!t.stream2) {
+            DG_CUDA(cudaStreamCreateWithFlags(&t.stream2, cudaStreamNonBlocking));
+            DG_CUDA(cudaEventCreateWithFlags(&t.ev_a, cudaEventDisableTiming));
+            DG_CUDA(cudaEventCreateWithFlags(&t.ev_b, cudaEventDisableTiming));
+        }
+        if (!t.stage_ev[0])
+            for (int k = 0; k < 4; k++) DG_CUDA(cudaEventCreateWithFlags(&t.stage_ev[k], cudaEventDisableTiming));
+        DG_CUDA(cudaEventRecord(t.ev_a, t.stream));         // the scratch may still be read by work queued on t.stream
+        DG_CUDA(cudaStreamWaitEvent(t.stream2, t.ev_a, 0));
+        stage.nchunks = 4;
+        for (int k = 0; k < 4; k++) {
+            stage.lo[k] = n * k / 4;
+            stage.lo[k + 1] = n * (k + 1) / 4;
+            stage.ev[k] = t.stage_ev[k];
+            const size_t lo = stage.lo[k], cnt = stage.lo[k + 1] - lo;
+            DG_CUDA(cudaMemcpyAsync(d_scalars + 32 * lo, scalars + 32 * lo, 32 * cnt, cudaMemcpyHostToDevice, t.stream2));
+            DG_CUDA(cudaEventRecord(stage.ev[k], t.stream2));
+        }
+    } else if (n) {
+        DG_CUDA(cudaMemcpyAsync(d_scalars, scalars, 32 * n, cudaMemcpyHostToDevice, t.stream));
+    }
     if (n && mont_scalars) fr_into_bigint_device(d_scalars, d_scalars, n, t.stream);   // msm_unchecked: into_bigint first
     if (!handle && n) {
         uint8_t *d_bases = t.arena.alloc<uint8_t>(PT * n);
@@ -225,8 +252,8 @@ static int32_t msm_host(uint64_t handle, const uint8_t *bases, const uint8_t *sc
         bases_dev = d_bases;
     }
     char *scratch = t.arena.alloc<char>(need - t.arena.used);
-    rc = G2 ? msm_run_g2(bases_dev, d_scalars, n, d_out, scratch, t.err_flag, t.stream, pre)
-            : msm_run_g1(bases_dev, d_scalars, n, d_out, scratch, t.err_flag, t.stream, pre);
+    rc = G2 ? msm_run_g2(bases_dev, d_scalars, n, d_out, scratch, t.err_flag, t.stream, pre, chunked ? &stage : nullptr)
+            : msm_run_g1(bases_dev, d_scalars, n, d_out, scratch, t.err_flag, t.stream, pre, chunked ? &stage : nullptr);
     if (rc) return rc;
     if (!out_keep_dev) DG_CUDA(cudaMemcpyAsync(out_jac, d_out, JAC, cudaMemcpyDeviceToHost, t.stream));
     return read_err_flag(t, t.stream, "msm");

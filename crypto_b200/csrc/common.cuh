@@ -98,6 +98,7 @@ struct ThreadState {
     cudaStream_t stream = nullptr;
     cudaStream_t stream2 = nullptr;   // second stream for calls that overlap independent MSMs (dg_groth16_prove_msms); created on first use
     cudaEvent_t ev_a = nullptr, ev_b = nullptr;
+    cudaEvent_t stage_ev[4] = {};     // chunked scalar staging of the host MSM path (capi.cu msm_host)
     int slot = 0;                     // device slot this thread drives: 0 for callers, d for the worker of devices[d]
     Arena arena;
     std::string err;
@@ -153,10 +154,14 @@ size_t msm_scratch_bytes_g1(size_t n, MsmPre pre);
 size_t msm_scratch_bytes_g2(size_t n, MsmPre pre);
 void msm_plan_g1(size_t n, MsmPre pre, int *c, int *rounds);
 void msm_plan_g2(size_t n, MsmPre pre, int *c, int *rounds);
+// Scalars that are still arriving from the host: chunk k = [lo[k], lo[k + 1]) is on the device once ev[k] has fired (the
+// copies run on a second stream).  The histogram pass of the digit kernel is launched per chunk behind its event, so the
+// PCIe transfer of chunk k + 1 overlaps the counting of chunk k.
+struct MsmStage { int nchunks; cudaEvent_t ev[4]; size_t lo[5]; };
 int32_t msm_run_g1(const void *bases_dev, const void *scalars_dev, size_t n, void *out_jac_dev, char *scratch,
-                   uint32_t *err_flag, cudaStream_t s, MsmPre pre);
+                   uint32_t *err_flag, cudaStream_t s, MsmPre pre, const MsmStage *stage = nullptr);
 int32_t msm_run_g2(const void *bases_dev, const void *scalars_dev, size_t n, void *out_jac_dev, char *scratch,
-                   uint32_t *err_flag, cudaStream_t s, MsmPre pre);
+                   uint32_t *err_flag, cudaStream_t s, MsmPre pre, const MsmStage *stage = nullptr);
 void ntt_release_plans();                                                                  // ntt.cu
 int32_t fr_into_bigint_device(const void *in, void *out, size_t n, cudaStream_t s);   // ntt.cu
 // Partial results of a sharded MSM, one Jacobian record per device; entries may point into peer memory (NVLink).

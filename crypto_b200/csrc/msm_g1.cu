@@ -8,8 +8,8 @@ void msm_plan_g1(size_t n, MsmPre pre, int *c, int *rounds) {
     *rounds = m.R;
 }
 int32_t msm_run_g1(const void *bases_dev, const void *scalars_dev, size_t n, void *out_jac_dev, char *scratch,
-                   uint32_t *err_flag, cudaStream_t s, MsmPre pre) {
-    return msm_run<Fp>(bases_dev, scalars_dev, n, out_jac_dev, scratch, err_flag, s, pre);
+                   uint32_t *err_flag, cudaStream_t s, MsmPre pre, const MsmStage *stage) {
+    return msm_run<Fp>(bases_dev, scalars_dev, n, out_jac_dev, scratch, err_flag, s, pre, stage);
 }
 int32_t glv_expand_g1(const void *in, size_t n, void *out, size_t phi_off, cudaStream_t s) {
     if (n) DG_LAUNCH(k_glv_expand<Fp>, div_up(n, 256), 256, 0, s, (const Affine<Fp> *)in, (uint32_t)n, (Affine<Fp> *)out, (uint32_t)phi_off);

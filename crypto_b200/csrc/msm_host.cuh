@@ -84,7 +84,8 @@ template <class F> static inline MsmLayout msm_layout(size_t n, MsmPre pre) {
     int min_waves = ctx().tunable[0].load();
     if (min_waves < 1) min_waves = 1;
     size_t kmax = ctx().tunable[3].load() > 0 ? (size_t)ctx().tunable[3].load() : 128;
-    const size_t ba_threads = (size_t)ctx().sm_count * (sizeof(F) > 48 ? 2 : 4) * DG_BA_THREADS;     // one resident wave
+    const int occ5 = sizeof(F) == 48 && ctx().tunable[6].load() == 5;
+    const size_t ba_threads = (size_t)ctx().sm_count * (sizeof(F) > 48 ? 2 : (occ5 ? 5 : 4)) * DG_BA_THREADS;     // one resident wave
     for (int r = 0; r < m.R; r++) {
         size_t waves = (m.mb[r + 1] + ba_threads * kmax - 1) / (ba_threads * kmax);
         if (waves < (size_t)min_waves) waves = min_waves;
@@ -151,7 +152,7 @@ template <class F> __global__ void k_set_jac_inf(Jac<F> *out) {
 
 template <class F>
 static int32_t msm_run(const void *bases_dev, const void *scalars_dev, size_t n, void *out_jac_dev, char *scratch,
-                       uint32_t *err_flag, cudaStream_t s, MsmPre pre) {
+                       uint32_t *err_flag, cudaStream_t s, MsmPre pre, const MsmStage *stage = nullptr) {
     // The flag reports THIS run: a stale bit from an earlier asynchronous call must not fail a valid one.
     DG_CUDA(cudaMemsetAsync(err_flag, 0, 4, s));
     if (n == 0) {
@@ -190,7 +191,15 @@ static int32_t msm_run(const void *bases_dev, const void *scalars_dev, size_t n,
 
     DG_CUDA(cudaMemsetAsync(hist, 0, sizeof(uint32_t) * g.nb, s));
     unsigned gd = div_up(n, 256);
-    DG_LAUNCH(k_digits<0>, gd, 256, 0, s, (const uint32_t *)scalars_dev, (uint32_t)n, g, hist, (uint32_t *)nullptr, err_flag);
+    if (stage && stage->nchunks > 1) {
+        for (int k = 0; k < stage->nchunks; k++) {          // count each chunk as soon as its copy has landed
+            const size_t lo = stage->lo[k], cnt = stage->lo[k + 1] - lo;
+            DG_CUDA(cudaStreamWaitEvent(s, stage->ev[k], 0));
+            if (cnt) DG_LAUNCH(k_digits<0>, div_up(cnt, 256), 256, 0, s, (const uint32_t *)scalars_dev + 8 * lo, (uint32_t)cnt, g, hist, (uint32_t *)nullptr, err_flag);
+        }
+    } else {
+        DG_LAUNCH(k_digits<0>, gd, 256, 0, s, (const uint32_t *)scalars_dev, (uint32_t)n, g, hist, (uint32_t *)nullptr, err_flag);
+    }
     unsigned sb = div_up(g.nb, DG_SCAN_ITEMS);
     DG_LAUNCH(k_scan_blocks, sb, 1024, 0, s, hist, off, bsums, g.nb);
     DG_LAUNCH(k_scan_sums, 1, 1024, 0, s, bsums, sb);
@@ -225,6 +234,10 @@ static int32_t msm_run(const void *bases_dev, const void *scalars_dev, size_t n,
             {
                 auto kg = k_affine_round<F, true>;
                 auto kd = k_affine_round<F, false>;
+                if (sizeof(F) == 48 && ctx().tunable[6].load() == 5) {          // experiment: 5 CTAs / SM at 96 registers
+                    kg = k_affine_round<F, true, 5>;
+                    kd = k_affine_round<F, false, 5>;
+                }
                 if (r == 0) DG_LAUNCH(kg, m.ctas[r], DG_BA_THREADS, 0, s, src, entries, off_in, off_out, g.nb, m.K[r], dst, pre_scratch);
                 else DG_LAUNCH(kd, m.ctas[r], DG_BA_THREADS, 0, s, src, (const uint32_t *)nullptr, off_in, off_out, g.nb, m.K[r], dst, pre_scratch);
             }
