@@ -222,7 +222,7 @@ static int32_t msm_host(uint64_t handle, const uint8_t *bases, const uint8_t *sc
     // Large inputs arrive in four chunks on a second stream so the PCIe transfer overlaps the histogram pass (pinned
     // host memory makes the copies truly asynchronous; pageable memory still works, without the overlap).
     MsmStage stage = {1, {}, {0, n, n, n, n}};
-    const bool chunked = n >= (1u << 18) && !mont_scalars;
+    const bool chunked = n >= (1u << 18) && !mont_scalars && ctx().tunable[7].load() == 0;      // tunable 7: A/B switch
     if (chunked) {
         if (!t.stream2) {
             DG_CUDA(cudaStreamCreateWithFlags(&t.stream2, cudaStreamNonBlocking));

@@ -84,8 +84,7 @@ template <class F> static inline MsmLayout msm_layout(size_t n, MsmPre pre) {
     int min_waves = ctx().tunable[0].load();
     if (min_waves < 1) min_waves = 1;
     size_t kmax = ctx().tunable[3].load() > 0 ? (size_t)ctx().tunable[3].load() : 128;
-    const int occ5 = sizeof(F) == 48 && ctx().tunable[6].load() == 5;
-    const size_t ba_threads = (size_t)ctx().sm_count * (sizeof(F) > 48 ? 2 : (occ5 ? 5 : 4)) * DG_BA_THREADS;     // one resident wave
+    const size_t ba_threads = (size_t)ctx().sm_count * (sizeof(F) > 48 ? 2 : 4) * DG_BA_THREADS;     // one resident wave
     for (int r = 0; r < m.R; r++) {
         size_t waves = (m.mb[r + 1] + ba_threads * kmax - 1) / (ba_threads * kmax);
         if (waves < (size_t)min_waves) waves = min_waves;
@@ -234,10 +233,6 @@ static int32_t msm_run(const void *bases_dev, const void *scalars_dev, size_t n,
             {
                 auto kg = k_affine_round<F, true>;
                 auto kd = k_affine_round<F, false>;
-                if (sizeof(F) == 48 && ctx().tunable[6].load() == 5) {          // experiment: 5 CTAs / SM at 96 registers
-                    kg = k_affine_round<F, true, 5>;
-                    kd = k_affine_round<F, false, 5>;
-                }
                 if (r == 0) DG_LAUNCH(kg, m.ctas[r], DG_BA_THREADS, 0, s, src, entries, off_in, off_out, g.nb, m.K[r], dst, pre_scratch);
                 else DG_LAUNCH(kd, m.ctas[r], DG_BA_THREADS, 0, s, src, (const uint32_t *)nullptr, off_in, off_out, g.nb, m.K[r], dst, pre_scratch);
             }

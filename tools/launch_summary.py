@@ -7,7 +7,8 @@ rows = [r for r in csv.reader(open(sys.argv[1])) if len(r) > 10]
 hdr = rows[0]
 ki, vi, ui = hdr.index('Kernel Name'), hdr.index('Metric Value'), hdr.index('Metric Unit')
 data = [(r[ki], float(r[vi].replace(',', '')) * {'ns': 1e-3, 'us': 1.0, 'ms': 1e3}.get(r[ui], 1e-3)) for r in rows[1:]]
-starts = [i for i, (k, _) in enumerate(data) if 'k_digits<0>' in k]
+# a step starts at a k_digits<0> launch that does not directly follow another one (the host path counts in four chunks)
+starts = [i for i, (k, _) in enumerate(data) if 'k_digits<0>' in k and (i == 0 or 'k_digits<0>' not in data[i - 1][0])]
 steps = []
 for a, b in zip(starts, starts[1:] + [len(data)]):
     steps.append(data[a:b])

@@ -16,8 +16,6 @@ bases = cref.g2_generator_muls(ks) if G2 else cref.g1_generator_muls(ks)
 lib.init()
 if len(sys.argv) > 4:
     lib.dbg_set_tunable(0, int(sys.argv[4]))
-if os.environ.get("DG_OCC5"):
-    lib.dbg_set_tunable(6, 5)
 if len(sys.argv) > 6:
     lib.dbg_set_tunable(3, int(sys.argv[6]))
 d_s = torch.from_numpy(sc).cuda(); d_o = torch.zeros(288 if G2 else 144, dtype=torch.uint8, device='cuda')
