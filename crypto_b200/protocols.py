@@ -167,6 +167,13 @@ class PoKOfSignatureG1Proof:
     T2: bytes
     sc_resp_2: SchnorrResponse
 
+    def get_resp_for_message(self, msg_idx, revealed_msg_ids):
+        """Schnorr response of hidden message msg_idx (proof.rs:448-476): its position among the hidden messages."""
+        if msg_idx in revealed_msg_ids:
+            raise ValueError('InvalidMsgIdxForResponse')
+        pos = msg_idx - sum(1 for i in revealed_msg_ids if i < msg_idx)
+        return self.sc_resp_2.responses[pos]
+
     def verify_schnorr_proofs(self, revealed_msgs: Dict[int, int], challenge, params: SignatureParamsG1):
         A_bar_minus_d = gp.into_affine(gp.add_affine([self.A_bar, gp.neg(self.d)]))
         if not self.sc_resp_1.verify(A_bar_minus_d, self.A_prime, params.h_0, challenge):
@@ -199,7 +206,9 @@ class PoKOfSignatureG1Protocol:
     """proof.rs:159-251.  `revealed` = indices disclosed to the verifier; rnd = the prover's random scalars
     (r1, r2, blinding for -e, blinding for r2, one blinding per hidden message, blinding for -r3, blinding for s')."""
 
-    def __init__(self, signature: SignatureG1, params: SignatureParamsG1, messages: List[int], revealed, rnd):
+    def __init__(self, signature: SignatureG1, params: SignatureParamsG1, messages: List[int], revealed, rnd, blindings=None):
+        """blindings: {message index: blinding} for MessageOrBlinding::BlindMessageWithConcreteBlinding (witness equalities
+        across statements reuse one blinding); every other hidden message draws its blinding from rnd."""
         n = params.supported_message_count()
         if len(messages) != n:
             raise ValueError('MessageCountIncompatibleWithSigParams')
@@ -219,7 +228,8 @@ class PoKOfSignatureG1Protocol:
         self.sc_comm_1 = PokPedersenCommitmentProtocol(-signature.e % R_MODULUS, next(rnd), A_prime, r2, next(rnd), params.h_0)
         hidden = [i for i in range(n) if i not in revealed]
         bases_2 = b''.join(params.h_at(i) for i in hidden) + self.d + params.h_0
-        randomness_2 = [next(rnd) for _ in hidden] + [next(rnd), next(rnd)]
+        blindings = blindings or {}
+        randomness_2 = [blindings[i] if i in blindings else next(rnd) for i in hidden] + [next(rnd), next(rnd)]
         self.sc_wits_2 = [messages[i] for i in hidden] + [-r3 % R_MODULUS, s_prime]
         self.sc_comm_2 = SchnorrCommitment.new(bases_2, randomness_2)
 

@@ -195,6 +195,49 @@ template <class G> struct VariableBaseMSM {
     }
 };
 
+// ---- one process, several GPUs (dg_init_devices / dg_msm_*_sharded) ------------------------------
+// The reference is one process with rayon threads; this is the entry point its glue would call for the large MSMs.
+inline void init_devices(const std::vector<int> &devices) {
+    std::vector<int32_t> d(devices.begin(), devices.end());
+    check(dg_init_devices(d.data(), (int32_t)d.size()));
+}
+inline int device_count() { int32_t n = 0; check(dg_device_count(&n)); return n; }
+// Bases resident on every device of init_devices, split by contiguous ranges (RAII over the sharded handle)
+class ShardedBasesG1 {
+  public:
+    explicit ShardedBasesG1(const std::vector<G1::Affine> &bases) : n(bases.size()) {
+        check(dg_bases_upload_g1_sharded(bases[0].b.data(), bases.size(), &handle));
+    }
+    ~ShardedBasesG1() { if (handle) dg_bases_free(handle); }
+    ShardedBasesG1(const ShardedBasesG1 &) = delete;
+    ShardedBasesG1 &operator=(const ShardedBasesG1 &) = delete;
+    void precompute(int window_bits = 0) { check(dg_bases_precompute(handle, window_bits)); }
+    // msm_bigint over a prefix of the resident bases: truncates to the shorter side like arkworks
+    G1::Projective msm_bigint(const std::vector<Fr> &bigints) const {
+        size_t k = bigints.size() < n ? bigints.size() : n;
+        G1::Projective out;
+        check(dg_msm_g1_sharded(handle, nullptr, k ? bigints[0].bytes() : nullptr, k, out.b.data()));
+        return out;
+    }
+    uint64_t handle = 0;
+    size_t n;
+};
+inline G1::Projective msm_bigint_sharded(const std::vector<G1::Affine> &bases, const std::vector<Fr> &bigints) {
+    size_t n = bases.size() < bigints.size() ? bases.size() : bigints.size();
+    G1::Projective out;
+    check(dg_msm_g1_sharded(0, n ? bases[0].b.data() : nullptr, n ? bigints[0].bytes() : nullptr, n, out.b.data()));
+    return out;
+}
+
+// ---- fused accumulator witness update (vb_accumulator/src/witness.rs:269-284): d_i * C_i + v_i * V, normalised ------
+inline std::vector<G1::Affine> batch_mul_add_same(const std::vector<G1::Affine> &c, const std::vector<Fr> &d, const G1::Affine &v,
+                                                  const std::vector<Fr> &vf) {
+    if (c.size() != d.size() || d.size() != vf.size()) throw Error(DG_ERR_BAD_ARG, "NeedSameNoOfElementsAndWitnesses");
+    std::vector<G1::Affine> out(c.size());
+    if (!c.empty()) check(dg_batch_mul_add_same_g1(c[0].b.data(), d[0].bytes(), v.b.data(), vf[0].bytes(), c.size(), out[0].b.data()));
+    return out;
+}
+
 // ---- utils::msm::WindowTable -------------------------------------------------------------------------
 inline size_t ln_without_floats(size_t a) { size_t l = 0; while ((size_t(1) << l) < a) l++; return l * 69 / 100; }
 template <class G> class WindowTable {

@@ -197,6 +197,43 @@ static void test_concurrent_callers() {
     for (int t = 0; t < 4; t++) CHECK(okv[t]);
 }
 
+// one process, several GPUs + the table-free fused update (SURVEY.md 8b "dg_msm_g1_sharded", row a16)
+static void test_sharded_and_fused() {
+    dg_shutdown();
+    int nd = 1;
+    try { init_devices({0, 1}); nd = 2; } catch (const Error &) { init_devices({0}); }
+    CHECK(device_count() == nd);
+    const size_t n = 5000;
+    auto g = rand_g1(n);
+    std::vector<Fr> e(n); for (auto &x : e) x = rand_fr();
+    uint8_t jac[144]; G1Affine exp;
+    ref_msm_g1(g[0].b.data(), e[0].bytes(), n, jac); ref_normalize_batch_g1(jac, 1, exp.b.data());
+    CHECK(into_affine<G1>(msm_bigint_sharded(g, e)) == exp);
+    {
+        ShardedBasesG1 hb(g);
+        CHECK(into_affine<G1>(hb.msm_bigint(e)) == exp);
+        hb.precompute();
+        CHECK(into_affine<G1>(hb.msm_bigint(e)) == exp);
+        std::vector<Fr> half(e.begin(), e.begin() + n / 2);                 // prefix: the second shard goes empty
+        ref_msm_g1(g[0].b.data(), e[0].bytes(), n / 2, jac); G1Affine exp2; ref_normalize_batch_g1(jac, 1, exp2.b.data());
+        CHECK(into_affine<G1>(hb.msm_bigint(half)) == exp2);
+    }
+    CHECK(msm_bigint_sharded({}, {}).is_zero());
+    // d_i * C_i + v_i * V == the 2-term MSM of the oracle
+    const size_t m = 40;
+    auto c = rand_g1(m); auto v = rand_g1(1)[0];
+    std::vector<Fr> d(m), vf(m); for (size_t i = 0; i < m; i++) { d[i] = rand_fr(); vf[i] = rand_fr(); }
+    auto out = batch_mul_add_same(c, d, v, vf);
+    for (size_t i = 0; i < m; i++) {
+        G1Affine two[2] = {c[i], v}; Fr sc[2] = {d[i], vf[i]};
+        ref_msm_g1(two[0].b.data(), sc[0].bytes(), 2, jac); G1Affine ex; ref_normalize_batch_g1(jac, 1, ex.b.data());
+        CHECK(out[i] == ex);
+    }
+    bool threw = false;
+    try { d.pop_back(); batch_mul_add_same(c, d, v, vf); } catch (const Error &) { threw = true; }
+    CHECK(threw);
+}
+
 int main() {
     init(0);
     test_wire_formats();
@@ -205,6 +242,7 @@ int main() {
     test_window_table_and_msm();
     test_pairing_randomize();
     test_mult_checker();
+    test_sharded_and_fused();
     std::printf("cpp host api ok, launches=%llu\n", (unsigned long long)dg_launch_count());
     return 0;
 }
