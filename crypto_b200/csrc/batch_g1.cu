@@ -43,6 +43,7 @@ int32_t dg_batch_mul_add_same_g1(const uint8_t *p, const uint8_t *sa, const uint
     if (!v) return fail(DG_ERR_BAD_ARG, "batch_mul_add_same: null pointer");
     return batch_mul_add_fixed<Fp>(p, sa, 0, sb, m, o, v);
 }
+int32_t dg_compress_g1(const uint8_t *l, const uint8_t *r, size_t m, const uint8_t *s, uint8_t *o) { return compress_host<Fp>(l, r, m, s, o); }
 int32_t dg_normalize_batch_g1(const uint8_t *j, size_t m, uint8_t *o) { return normalize_host<Fp>(j, m, o); }
 int32_t dg_fold_g1(const uint8_t *j, size_t k, uint8_t *o) { return fold_host<Fp>(j, k, o); }
 int32_t dg_fold_g1_device(const void *j, size_t k, void *o, void *stream) {

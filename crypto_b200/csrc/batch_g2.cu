@@ -14,6 +14,7 @@ int32_t dg_fixed_base_table_g2(const uint8_t *p, size_t hint_n, uint64_t *h) { r
 int32_t dg_fixed_base_mul_many_g2(uint64_t h, const uint8_t *s, size_t m, uint8_t *o) { return fixed_mul_many<Fp2>(h, s, m, o); }
 int32_t dg_fixed_base_mul_many_normalized_g2(uint64_t h, const uint8_t *s, size_t m, uint8_t *o) { return fixed_mul_many_normalized<Fp2>(h, s, m, o); }
 int32_t dg_batch_mul_g2(const uint8_t *p, const uint8_t *s, size_t m, uint8_t *o) { return batch_mul<Fp2>(p, s, m, o); }
+int32_t dg_compress_g2(const uint8_t *l, const uint8_t *r, size_t m, const uint8_t *s, uint8_t *o) { return compress_host<Fp2>(l, r, m, s, o); }
 int32_t dg_normalize_batch_g2(const uint8_t *j, size_t m, uint8_t *o) { return normalize_host<Fp2>(j, m, o); }
 int32_t dg_fold_g2(const uint8_t *j, size_t k, uint8_t *o) { return fold_host<Fp2>(j, k, o); }
 }

@@ -129,6 +129,31 @@ template <class F> static int32_t batch_mul(const uint8_t *points, const uint8_t
 }
 
 // v_affine != nullptr: V given directly, no window table (always the joint form)
+// out[i] = normalize(left[i] + [scalar] right[i]): utils::compress and Key::compress of the SnarkPack aggregation
+// (legogroth16/src/aggregation/utils.rs:26-37, key.rs:118-143), one launch for the whole half-vector.
+template <class F> static int32_t compress_host(const uint8_t *left, const uint8_t *right, size_t m, const uint8_t *scalar, uint8_t *out_affine) {
+    int32_t rc = check_init();
+    if (rc) return rc;
+    if (m && (!left || !right || !scalar || !out_affine)) return fail(DG_ERR_BAD_ARG, "compress: null pointer");
+    if (m == 0) return DG_OK;
+    ThreadState &t = tls();
+    rc = t.arena.ensure(3 * Arena::pad(Sizes<F>::AFF * m) + Arena::pad(256) + Arena::pad(Sizes<F>::JAC * m) + Arena::pad(sizeof(F) * m), t.stream);
+    if (rc) return rc;
+    Affine<F> *d_l = t.arena.alloc<Affine<F>>(m), *d_r = t.arena.alloc<Affine<F>>(m), *d_a = t.arena.alloc<Affine<F>>(m);
+    uint8_t *d_s = t.arena.alloc<uint8_t>(32);
+    Jac<F> *d_o = t.arena.alloc<Jac<F>>(m);
+    F *d_prefix = t.arena.alloc<F>(m);
+    DG_CUDA(cudaMemcpyAsync(d_l, left, Sizes<F>::AFF * m, cudaMemcpyHostToDevice, t.stream));
+    DG_CUDA(cudaMemcpyAsync(d_r, right, Sizes<F>::AFF * m, cudaMemcpyHostToDevice, t.stream));
+    DG_CUDA(cudaMemcpyAsync(d_s, scalar, 32, cudaMemcpyHostToDevice, t.stream));
+    DG_LAUNCH(k_batch_mul<F>, div_up(m, 128), 128, 0, t.stream, d_r, d_s, (uint32_t)m, d_o, ctx().tunable[4].load() == 0 ? 1 : 0, 1,
+              (const Affine<F> *)d_l);
+    normalize_device<F>(d_o, m, d_a, d_prefix, t.stream);
+    DG_CUDA(cudaMemcpyAsync(out_affine, d_a, Sizes<F>::AFF * m, cudaMemcpyDeviceToHost, t.stream));
+    DG_CUDA(cudaStreamSynchronize(t.stream));
+    return DG_OK;
+}
+
 template <class F>
 static int32_t batch_mul_add_fixed(const uint8_t *points, const uint8_t *sa, uint64_t handle, const uint8_t *sb, size_t m,
                                    uint8_t *out_affine, const uint8_t *v_affine = nullptr) {

@@ -217,13 +217,16 @@ template <class F> __global__ void k_w4_table(const Affine<F> *v, JacZ<F> *out) 
 
 template <class F>
 __global__ void __launch_bounds__(128) k_batch_mul(const Affine<F> *__restrict__ points, const uint8_t *__restrict__ scalars,
-                                                   uint32_t m, Jac<F> *__restrict__ out, int glv) {
+                                                   uint32_t m, Jac<F> *__restrict__ out, int glv, int one_scalar = 0,
+                                                   const Affine<F> *__restrict__ add = nullptr) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= m) return;
     uint32_t s[9];
-    load_scalar(scalars, i, s);
+    load_scalar(scalars, one_scalar ? 0 : i, s);           // one_scalar: every point is multiplied by scalars[0]
     Affine<F> p = aff_load<F>(&points[i]);
-    jac_store(&out[i], scalar_mul_w4(p, s, glv));
+    Jac<F> r = scalar_mul_w4(p, s, glv);
+    if (add) r = jac_madd(r, aff_load<F>(&add[i]));        // + add[i]: the "compress" step of the SnarkPack GIPA rounds
+    jac_store(&out[i], r);
 }
 
 // ---- fixed-base tables -------------------------------------------------------------------------

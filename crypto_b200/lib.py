@@ -27,7 +27,7 @@ EXPORTS = [
     'dg_fixed_base_table_download', 'dg_fixed_base_table_free',
     'dg_fixed_base_mul_many_g1', 'dg_fixed_base_mul_many_g2',
     'dg_fixed_base_mul_many_normalized_g1', 'dg_fixed_base_mul_many_normalized_g2',
-    'dg_batch_mul_g1', 'dg_batch_mul_g2', 'dg_batch_mul_add_fixed_g1', 'dg_batch_mul_add_same_g1',
+    'dg_batch_mul_g1', 'dg_batch_mul_g2', 'dg_batch_mul_add_fixed_g1', 'dg_batch_mul_add_same_g1', 'dg_compress_g1', 'dg_compress_g2',
     'dg_normalize_batch_g1', 'dg_normalize_batch_g2',
     'dg_multi_miller_loop', 'dg_final_exponentiation', 'dg_multi_pairing', 'dg_multi_pairing_is_one', 'dg_multi_pairing_batch',
     'dg_gt_pow', 'dg_fp12_mul',
@@ -353,6 +353,20 @@ def batch_mul_add_same_g1(points, scalars_a, v_affine, scalars_b):
     o, op = _out(G1_AFF * m)
     _check(lib.dg_batch_mul_add_same_g1(pp, ap, vp, bp, C.c_size_t(m), op))
     return o[:G1_AFF * m]
+
+
+def compress(left, right, scalar, g2=False):
+    """left[i] + [scalar] right[i], normalised (dg_compress_*)."""
+    lib = init()
+    l, lp = _in(left); r, rp = _in(right); s, sp = _in(scalar)
+    rec = G2_AFF if g2 else G1_AFF
+    m = l.size // rec
+    if l.size != r.size or l.size % rec or s.size != SCALAR:
+        raise ValueError('compress: left and right must hold the same number of points, scalar 32 bytes')
+    o, op = _out(rec * m)
+    fn = lib.dg_compress_g2 if g2 else lib.dg_compress_g1
+    _check(fn(lp, rp, C.c_size_t(m), sp, op))
+    return o[:rec * m]
 
 
 def normalize_batch(jac, g2=False):

@@ -170,6 +170,11 @@ int32_t dg_batch_mul_add_fixed_g1(const uint8_t *points_affine, const uint8_t *s
 int32_t dg_batch_mul_add_same_g1(const uint8_t *points_affine, const uint8_t *scalars_a, const uint8_t *v_affine,
                                  const uint8_t *scalars_b, size_t m, uint8_t *out_affine);
 
+/* out[i] = normalize(left[i] + [scalar] right[i]), one scalar for the whole vector: utils::compress and Key::compress of
+ * the SnarkPack GIPA rounds (legogroth16/src/aggregation/utils.rs:26-37, key.rs:118-143; "next" row f3). */
+int32_t dg_compress_g1(const uint8_t *left_affine, const uint8_t *right_affine, size_t m, const uint8_t *scalar, uint8_t *out_affine);
+int32_t dg_compress_g2(const uint8_t *left_affine, const uint8_t *right_affine, size_t m, const uint8_t *scalar, uint8_t *out_affine);
+
 /* ---- CurveGroup::normalize_batch ------------------------------------------------------------
  * (vb_accumulator/src/witness.rs:193,232,284; batch_utils.rs:506,524,633,651). */
 int32_t dg_normalize_batch_g1(const uint8_t *jac, size_t m, uint8_t *out_affine);
