@@ -38,6 +38,37 @@ t.free()
 ok &= bytes(lib.multi_pairing(bases[:96 * 2], b2[:192 * 2])) == bytes(cref.multi_pairing(bases[:96 * 2], b2[:192 * 2]))
 d = cref.random_scalars(1 << 10, 5)
 ok &= bytes(lib.fr_ntt(d, 10, False, True)) == bytes(cref.fr_ntt(d, 10, False, True))
+# ---- round 2: GLV on / off, sharded entry point, windowed batch multiplication (GLV and generic chain), fused update
+# (joint chain and table), Pornin inversion, compress, chained Groth16 prover on two streams
+lib.dbg_set_tunable(4, 1)
+ok &= bytes(cref.normalize_batch_g1(lib.msm(bases, ss))) == bytes(cref.normalize_batch_g1(cref.msm_g1(bases, ss)))
+lib.dbg_set_tunable(4, 0)
+ok &= bytes(cref.normalize_batch_g1(lib.msm_sharded(bases, ss))) == bytes(cref.normalize_batch_g1(cref.msm_g1(bases, ss)))
+hs = lib.ShardedBases(bases); hs.precompute(10)
+ok &= bytes(cref.normalize_batch_g1(lib.msm_sharded(hs, ss))) == bytes(cref.normalize_batch_g1(cref.msm_g1(bases, ss)))
+hs.free()
+big = np.array(ss[:32 * 40]); big[:32] = 0xff; big[31] = 0x7f          # one integer >= r: generic 65-digit chain
+ok &= bytes(cref.normalize_batch_g1(lib.batch_mul(bases[:96 * 40], big))) == bytes(cref.normalize_batch_g1(cref.batch_mul_g1(bases[:96 * 40], big)))
+ok &= bytes(cref.normalize_batch_g2(lib.batch_mul(b2, ss[:32 * 40], g2=True))) == bytes(cref.normalize_batch_g2(cref.batch_mul_g2(b2, ss[:32 * 40])))
+tv = lib.FixedBaseTable(bases[:96], 40)
+lib.dbg_set_tunable(5, 2)
+u_tab = bytes(lib.batch_mul_add_fixed_g1(bases[:96 * 40], ss[:32 * 40], tv, ss[32 * 40:32 * 80]))
+lib.dbg_set_tunable(5, 0)
+tv.free()
+ok &= u_tab == bytes(lib.batch_mul_add_same_g1(bases[:96 * 40], ss[:32 * 40], bases[:96], ss[32 * 40:32 * 80]))
+x48 = bases[:48 * 64]
+ok &= bytes(lib.dbg_fp_op(7, x48, x48)) == bytes(lib.dbg_fp_op(5, x48, x48))
+ok &= len(bytes(lib.compress(bases[:96 * 20], bases[96 * 20:96 * 40], ss[:32]))) == 96 * 20
+sys.path.insert(0, os.path.join(os.getcwd(), 'tools'))
+from crypto_b200 import groth16 as g16
+from oracle import bls12_381 as o
+from tools.synth_circuit import synthetic_r1cs
+cs, w = synthetic_r1cs(200, seed=4)
+pk, ni = g16.generate_parameters(cs, 11, 12, 13, 14, 15, 99991, o.g1_to_bytes(o.G1_GEN), o.g2_to_bytes(o.G2_GEN), 2)
+dpk = g16.DeviceProvingKey(pk, cs)
+proof, _ = g16.create_proof(dpk, w, 5, 6, 7)
+ok &= g16.verify_proof(g16.prepare_verifying_key(pk.vk), proof, w[1:ni])
+dpk.free()
 print('sanitizer workload ok =', bool(ok))
 PY
 for tool in memcheck racecheck; do
