@@ -27,6 +27,12 @@ namespace dg {
 #define PAIR_THREADS 128
 #define BLS_X_ABS 0xd201000000010000ULL
 
+// Logical worker id of a thread: workers 0, 1, 2, 3 are lane 0 of warps 0, 1, 2, 3, workers 4 .. 7 lane 1, and so on.
+// The engine's small linear stages give different workers different jobs ("worker 0: e = ..., worker 1: h = ...");
+// as lanes of ONE warp those jobs would run one after the other (divergence), as lanes of different warps they run
+// side by side on the four schedulers.  Every function below indexes its work by this id only.
+__device__ __forceinline__ int pair_wid() { return (int)((threadIdx.x & 31u) * 4u + (threadIdx.x >> 5)); }
+
 // Fp12 in shared/global memory: 12 Fp in ark order (c0.c0.c0, c0.c0.c1, c0.c1.c0, ..., c1.c2.c1).
 // Flattened basis: coefficient of w^k (an Fp2) lives at tower position (i = k&1, j = k>>1).
 struct F12 { Fp c[12]; };
@@ -35,11 +41,13 @@ __device__ __forceinline__ int widx(int k) { return (k & 1) * 6 + (k >> 1) * 2; 
 static __device__ __noinline__ Fp fp_mul_smem(const Fp *a, const Fp *b) { return fp_mul(*a, *b); }
 
 // One Karatsuba part of an Fp2 product: 0: a0*b0, 1: a1*b1, 2: (a0+a1)*(b0+b1)
+// ONE call site for the multiplier: with three calls in three branches the lanes of a warp holding parts 0, 1 and 2
+// would run the (out-of-line, ~600-instruction) multiplication three times in a row.
 __device__ __forceinline__ Fp fp2_part(int part, const Fp *a, const Fp *b) {
-    if (part == 0) return fp_mul_smem(a, b);
-    if (part == 1) return fp_mul_smem(a + 1, b + 1);
-    Fp sa = fp_add(a[0], a[1]), sb = fp_add(b[0], b[1]);
-    return fp_mul_smem(&sa, &sb);
+    Fp a0 = a[0], a1 = a[1], b0 = b[0], b1 = b[1];
+    Fp sa = fp_add(a0, a1), sb = fp_add(b0, b1);
+    Fp x = fsel(part == 2, sa, fsel(part == 1, a1, a0)), y = fsel(part == 2, sb, fsel(part == 1, b1, b0));
+    return fp_mul_smem(&x, &y);
 }
 // recombine three parts into the Fp2 product
 __device__ __forceinline__ void fp2_from_parts(Fp *d, const Fp *p) {
@@ -73,7 +81,7 @@ __device__ __forceinline__ Fp fp_half(const Fp &a) {
 //   phase 2:  36 lanes recombine their Fp2 product and apply the w^6 = xi twist when i + j >= 6
 //   phase 3:  12 lanes (degree k, component) add the six products of their column
 __device__ void f12_mul(Engine &e, F12 *C, const F12 *A, const F12 *B) {
-    int tid = threadIdx.x;
+    int tid = pair_wid();
     if (tid < 108) {
         int pr = tid / 3, part = tid - pr * 3, i = pr / 6, j = pr - i * 6;
         e.prod[tid] = fp2_part(part, &A->c[widx(i)], &B->c[widx(j)]);
@@ -84,12 +92,10 @@ __device__ void f12_mul(Engine &e, F12 *C, const F12 *A, const F12 *B) {
         const Fp *p = &e.prod[tid * 3];
         Fp c0 = fp_sub(p[0], p[1]);
         Fp c1 = fp_sub(fp_sub(p[2], p[0]), p[1]);
-        if (i + j >= 6) {                         // times xi = 1 + u
-            Fp t0 = fp_sub(c0, c1), t1 = fp_add(c0, c1);
-            c0 = t0; c1 = t1;
-        }
-        e.q[2 * tid] = c0;
-        e.q[2 * tid + 1] = c1;
+        Fp t0 = fp_sub(c0, c1), t1 = fp_add(c0, c1);      // times xi = 1 + u when i + j >= 6 (computed by every lane, selected)
+        const bool tw = i + j >= 6;
+        e.q[2 * tid] = fsel(tw, t0, c0);
+        e.q[2 * tid + 1] = fsel(tw, t1, c1);
     }
     __syncthreads();
     if (tid < 12) {
@@ -112,7 +118,7 @@ __device__ void f12_mul(Engine &e, F12 *C, const F12 *A, const F12 *B) {
 // (checked against the generic square in the big-integer oracle).  Nine Fp2 squarings = 18 Fp
 // multiplications in ONE wave of 18 lanes, then 12 lanes recombine.  C may alias A.
 __device__ void f12_cyc_sqr(Engine &e, F12 *C, const F12 *A) {
-    int tid = threadIdx.x;
+    int tid = pair_wid();
     if (tid < 18) {
         // lane = 2 s + h;  s = 3 m + j:  Fp4 number m (0: X, 1: Y, 2: Z), j = 0: x0, 1: x1, 2: x0 + x1
         int sidx = tid >> 1, h = tid & 1, m = sidx / 3, j = sidx - 3 * m;
@@ -137,19 +143,18 @@ __device__ void f12_cyc_sqr(Engine &e, F12 *C, const F12 *A) {
             return fp_add(S(3 * m, c), x);
         };
         auto part1 = [&](int m, int c) -> Fp { return fp_sub(fp_sub(S(3 * m + 2, c), S(3 * m, c)), S(3 * m + 1, c)); };
+        // Even k = 2m takes part 0 of the Fp4 square number m (minus sign); odd k takes part 1 of number
+        // (k == 1 ? 2 : (k - 3) / 2) (plus sign), times xi for k == 1.  With the worker numbering above the even and the
+        // odd outputs sit in different warps, and inside each branch the lanes differ only in data (m, comp).
         Fp v;
-        bool plus;
-        switch (k) {
-            case 0: v = part0(0, comp); plus = false; break;               // 3 X^2.0 - 2 a0
-            case 3: v = part1(0, comp); plus = true; break;                // 3 X^2.1 + 2 a3
-            case 2: v = part0(1, comp); plus = false; break;               // 3 Y^2.0 - 2 a2
-            case 5: v = part1(1, comp); plus = true; break;                // 3 Y^2.1 + 2 a5
-            case 4: v = part0(2, comp); plus = false; break;               // 3 Z^2.0 - 2 a4
-            default: {                                                     // k = 1: 3 xi Z^2.1 + 2 a1
-                Fp p0 = part1(2, 0), p1 = part1(2, 1);
-                v = comp ? fp_add(p0, p1) : fp_sub(p0, p1);
-                plus = true;
-            }
+        const bool plus = (k & 1) != 0;
+        if (!plus) {
+            v = part0(k >> 1, comp);
+        } else {
+            const int m = k == 1 ? 2 : (k - 3) >> 1;
+            Fp p0 = part1(m, 0), p1 = part1(m, 1);
+            Fp tw = comp ? fp_add(p0, p1) : fp_sub(p0, p1);                 // (xi * part1).comp
+            v = fsel(k == 1, tw, comp ? p1 : p0);
         }
         Fp three = fp_add(fp_dbl(v), v), two_a = fp_dbl(A->c[widx(k) + comp]);
         C->c[widx(k) + comp] = plus ? fp_add(three, two_a) : fp_sub(three, two_a);
@@ -158,24 +163,24 @@ __device__ void f12_cyc_sqr(Engine &e, F12 *C, const F12 *A) {
 }
 
 __device__ void f12_copy(F12 *d, const F12 *s) {
-    int tid = threadIdx.x;
+    int tid = pair_wid();
     if (tid < 12) d->c[tid] = s->c[tid];
     __syncthreads();
 }
 __device__ void f12_set_one(F12 *d) {
-    int tid = threadIdx.x;
+    int tid = pair_wid();
     if (tid < 12) d->c[tid] = tid == 0 ? fp_one() : fp_zero();
     __syncthreads();
 }
 // conjugation over Fp6 (= p^6 Frobenius): negate the w-odd half (tower c1 = indices 6..11)
 __device__ void f12_conj(F12 *d, const F12 *s) {
-    int tid = threadIdx.x;
+    int tid = pair_wid();
     if (tid < 12) d->c[tid] = tid < 6 ? s->c[tid] : fp_neg(s->c[tid]);
     __syncthreads();
 }
 // d = s^(p^pw), pw in {1,2,3}: coefficient of w^k -> conj^pw(a_k) * xi^(k (p^pw - 1)/6)
 __device__ void f12_frobenius(Engine &e, F12 *d, const F12 *s, int pw) {
-    int tid = threadIdx.x;
+    int tid = pair_wid();
     if (tid < 18) {
         int k = tid / 3, part = tid - k * 3;
         Fp a[2] = {s->c[widx(k)], s->c[widx(k) + 1]};
@@ -213,7 +218,7 @@ static __device__ __noinline__ Fp fp_inv_serial(const Fp &a) {
 // d = 1/s via norms:  abar = conj(s);  N = s*abar in Fp6;  N^-1 = sigma(N) sigma^2(N) / Norm_{Fp6/Fp2}(N)
 // with sigma = p^2 Frobenius;  the Fp2 norm is inverted with one Fp inversion.
 __device__ void f12_inv(Engine &e, F12 *d, const F12 *s, F12 *t0, F12 *t1, F12 *t2) {
-    int tid = threadIdx.x;
+    int tid = pair_wid();
     f12_conj(t0, s);                 // abar
     f12_mul(e, t1, s, t0);           // N (odd half is zero)
     f12_frobenius(e, t2, t1, 2);     // sigma(N)
@@ -291,7 +296,7 @@ __device__ __forceinline__ void fp2s_half(Fp *d, const Fp *a) { Fp x = fp_half(a
 // them is spread over several lanes instead of one.
 //   T layout (Fp2 = 2 slots): 0 m1=rx*ry  2 b  4 c  6 j  8 s  10 e  12 f  14 a  16 g  18 h  20 b-f
 __device__ void miller_double(Engine &e, MillerState &m) {
-    int tid = threadIdx.x;
+    int tid = pair_wid();
     Fp *T = e.tmp;
     // wave 1: 0: rx*ry  1: ry^2  2: rz^2  3: rx^2  4: (ry+rz)^2
     if (tid < 15) {
@@ -368,7 +373,7 @@ __device__ void miller_double(Engine &e, MillerState &m) {
 
 // Addition step (ark G2Prepared add_in_place), three product waves.
 __device__ void miller_add(Engine &e, MillerState &m) {
-    int tid = threadIdx.x;
+    int tid = pair_wid();
     Fp *T = e.tmp;   // 0: theta 2: lambda 4: c 6: d 8: e 10: f 12: g 14: h / (g-h)
     // wave 1: qy*rz, qx*rz
     if (tid < 6) {
@@ -452,7 +457,7 @@ __device__ void miller_add(Engine &e, MillerState &m) {
 
 // f *= ell(coeffs, P): line = c0 + (c1*px) v + (c2*py) v w  -> positions w^0, w^2, w^3
 __device__ void miller_ell(Engine &e, MillerState &m, F12 *f) {
-    int tid = threadIdx.x;
+    int tid = pair_wid();
     if (tid < 12) m.line.c[tid] = fp_zero();
     __syncthreads();
     if (tid < 2) m.line.c[widx(0) + tid] = m.co[0][tid];
@@ -472,7 +477,7 @@ struct PairSmem {
 __global__ void __launch_bounds__(PAIR_THREADS) k_miller(const Affine<Fp> *g1, const Affine<Fp2> *g2, uint32_t k, F12 *out) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     PairSmem &S = *reinterpret_cast<PairSmem *>(smem_raw);
-    int tid = threadIdx.x;
+    int tid = pair_wid();
     uint32_t pair = blockIdx.x;
     __shared__ int skip;
     if (tid == 0) {
@@ -503,7 +508,7 @@ __global__ void __launch_bounds__(PAIR_THREADS) k_miller(const Affine<Fp> *g1, c
 __global__ void __launch_bounds__(PAIR_THREADS) k_f12_reduce8(const F12 *in, uint32_t n, F12 *out) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     PairSmem &S = *reinterpret_cast<PairSmem *>(smem_raw);
-    int tid = threadIdx.x;
+    int tid = pair_wid();
     uint32_t lo = blockIdx.x * 8, hi = lo + 8 < n ? lo + 8 : n;
     if (tid < 12) S.f.c[tid] = fp_load_rw(&in[lo].c[tid]);
     __syncthreads();
@@ -521,7 +526,7 @@ __global__ void __launch_bounds__(PAIR_THREADS) k_f12_reduce8(const F12 *in, uin
 __global__ void __launch_bounds__(PAIR_THREADS) k_f12_finish(const F12 *in, int mode, F12 *out, int32_t *flags) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     PairSmem &S = *reinterpret_cast<PairSmem *>(smem_raw);
-    int tid = threadIdx.x;
+    int tid = pair_wid();
     __shared__ int is_zero;
     if (in) { if (tid < 12) S.f.c[tid] = fp_load_rw(&in->c[tid]); __syncthreads(); }
     else f12_set_one(&S.f);
@@ -546,7 +551,7 @@ __global__ void __launch_bounds__(PAIR_THREADS) k_f12_finish(const F12 *in, int 
 __global__ void __launch_bounds__(PAIR_THREADS) k_f12_mul_or_pow(const F12 *a, const F12 *b, const uint32_t *scalar, F12 *out) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     PairSmem &S = *reinterpret_cast<PairSmem *>(smem_raw);
-    int tid = threadIdx.x;
+    int tid = pair_wid();
     if (tid < 12) S.t[0].c[tid] = fp_load_rw(&a->c[tid]);
     __syncthreads();
     if (b) {
