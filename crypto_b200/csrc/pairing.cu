@@ -76,10 +76,45 @@ __device__ __forceinline__ Fp fp_half(const Fp &a) {
     return r;
 }
 
+// Unreduced accumulation for the linear stages: integers below 8p fit the 12 limbs (8p < 2^384), so up to six reduced
+// values are added as plain integers (one 12-limb carry chain each, no trial subtraction) and brought back below p by
+// three conditional subtractions of 4p, 2p, p -- about half the instructions of six modular additions, all of them on
+// the stage's critical path.
+__device__ __forceinline__ Fp fp_add_raw(const Fp &a, const Fp &b) {
+    Fp r;
+    asm volatile("add.cc.u32 %0, %1, %2;" : "=r"(r.l[0]) : "r"(a.l[0]), "r"(b.l[0]));
+#pragma unroll
+    for (int i = 1; i < 11; i++) asm volatile("addc.cc.u32 %0, %1, %2;" : "=r"(r.l[i]) : "r"(a.l[i]), "r"(b.l[i]));
+    asm volatile("addc.u32 %0, %1, %2;" : "=r"(r.l[11]) : "r"(a.l[11]), "r"(b.l[11]));
+    return r;
+}
+template <int K> __device__ __forceinline__ void fp_csub_kp(Fp &a) {          // a -= K p when a >= K p  (K = 1, 2, 4)
+    uint32_t t[12], br;
+    constexpr int SH = K == 4 ? 2 : K == 2 ? 1 : 0;
+    auto kp = [](int i) -> uint32_t {
+        uint64_t lo = i ? fp_p_limb(i - 1) : 0u, hi = fp_p_limb(i);
+        return SH ? (uint32_t)(((hi << 32) | lo) >> (32 - SH)) : (uint32_t)hi;
+    };
+    asm volatile("sub.cc.u32 %0, %1, %2;" : "=r"(t[0]) : "r"(a.l[0]), "r"(kp(0)));
+#pragma unroll
+    for (int i = 1; i < 12; i++) asm volatile("subc.cc.u32 %0, %1, %2;" : "=r"(t[i]) : "r"(a.l[i]), "r"(kp(i)));
+    asm volatile("subc.u32 %0, 0, 0;" : "=r"(br));
+    const bool keep = br != 0;
+#pragma unroll
+    for (int i = 0; i < 12; i++) a.l[i] = keep ? a.l[i] : t[i];
+}
+__device__ __forceinline__ Fp fp_reduce_lt8p(Fp a) {
+    fp_csub_kp<4>(a);
+    fp_csub_kp<2>(a);
+    fp_csub_kp<1>(a);
+    return a;
+}
+
 // C = A * B (C may alias A or B).  All PAIR_THREADS threads must call.
 //   phase 1: 108 lanes, one Fp multiplication each (36 Fp2 products x 3 Karatsuba parts)
-//   phase 2:  36 lanes recombine their Fp2 product and apply the w^6 = xi twist when i + j >= 6
-//   phase 3:  12 lanes (degree k, component) add the six products of their column
+//   phase 2:  72 lanes, one per component of the 36 Fp2 products, recombine the Karatsuba parts and apply the w^6 = xi
+//             twist when i + j >= 6 (two modular subtractions each)
+//   phase 3:  12 lanes (degree k, component) add the six products of their column unreduced and reduce once
 __device__ void f12_mul(Engine &e, F12 *C, const F12 *A, const F12 *B) {
     int tid = pair_wid();
     if (tid < 108) {
@@ -87,26 +122,25 @@ __device__ void f12_mul(Engine &e, F12 *C, const F12 *A, const F12 *B) {
         e.prod[tid] = fp2_part(part, &A->c[widx(i)], &B->c[widx(j)]);
     }
     __syncthreads();
-    if (tid < 36) {
-        int i = tid / 6, j = tid - i * 6;
-        const Fp *p = &e.prod[tid * 3];
-        Fp c0 = fp_sub(p[0], p[1]);
-        Fp c1 = fp_sub(fp_sub(p[2], p[0]), p[1]);
-        Fp t0 = fp_sub(c0, c1), t1 = fp_add(c0, c1);      // times xi = 1 + u when i + j >= 6 (computed by every lane, selected)
-        const bool tw = i + j >= 6;
-        e.q[2 * tid] = fsel(tw, t0, c0);
-        e.q[2 * tid + 1] = fsel(tw, t1, c1);
+    if (tid < 72) {                                       // one lane per COMPONENT of the 36 products (comp is warp-uniform)
+        int pr = tid >> 1, comp = tid & 1, i = pr / 6, j = pr - i * 6;
+        const Fp *p = &e.prod[pr * 3];
+        const bool tw = i + j >= 6;                       // times xi = 1 + u:  (c0 - c1, c0 + c1) = (2 p0 - p2, p2 - 2 p1)
+        Fp out;
+        if (comp == 0) out = fp_sub(fsel(tw, fp_dbl(p[0]), p[0]), fsel(tw, p[2], p[1]));
+        else out = fp_sub(fp_sub(p[2], fsel(tw, p[1], p[0])), p[1]);
+        e.q[tid] = out;
     }
     __syncthreads();
     if (tid < 12) {
         int k = tid >> 1, comp = tid & 1;
-        Fp acc = fp_zero();
+        Fp acc = e.q[2 * (0 * 6 + k) + comp];             // i = 0, j = k
 #pragma unroll
-        for (int i = 0; i < 6; i++) {
+        for (int i = 1; i < 6; i++) {
             int j = k - i; if (j < 0) j += 6;
-            acc = fp_add(acc, e.q[2 * (i * 6 + j) + comp]);
+            acc = fp_add_raw(acc, e.q[2 * (i * 6 + j) + comp]);
         }
-        C->c[widx(k) + comp] = acc;
+        C->c[widx(k) + comp] = fp_reduce_lt8p(acc);        // six reduced terms: < 6p
     }
     __syncthreads();
 }
@@ -313,38 +347,43 @@ __device__ void miller_double(Engine &e, MillerState &m) {
         e.prod[tid] = fp2_part(part, A, B);
     }
     __syncthreads();
-    if (tid < 5) fp2_from_parts(&T[2 * tid], &e.prod[3 * tid]);          // m1, b, c, j, s
-    __syncthreads();
-    if (tid == 0) {                                                        // e = (4+4u)*3c = 4*xi*3c ; f = 3e
-        Fp t3[2], ee[2], f[2];
-        fp2s_add(t3, &T[4], &T[4]); fp2s_add(t3, t3, &T[4]);
-        Fp x0 = fp_sub(t3[0], t3[1]), x1 = fp_add(t3[0], t3[1]);
-        ee[0] = fp_dbl(fp_dbl(x0)); ee[1] = fp_dbl(fp_dbl(x1));
-        fp2s_add(f, ee, ee); fp2s_add(f, f, ee);
-        T[10] = ee[0]; T[11] = ee[1]; T[12] = f[0]; T[13] = f[1];
-    } else if (tid == 1) {                                                 // h = s - (b + c) ; co2 = -h
-        Fp t3[2], h[2];
-        fp2s_add(t3, &T[2], &T[4]); fp2s_sub(h, &T[8], t3);
-        T[18] = h[0]; T[19] = h[1];
-        fp2s_neg(t3, h);
-        m.co[2][0] = t3[0]; m.co[2][1] = t3[1];
-    } else if (tid == 2) {                                                 // co1 = 3j
-        Fp t3[2];
-        fp2s_add(t3, &T[6], &T[6]); fp2s_add(t3, t3, &T[6]);
-        m.co[1][0] = t3[0]; m.co[1][1] = t3[1];
-    } else if (tid == 3) {                                                 // a = m1 / 2
-        fp2s_half(&T[14], &T[0]);
+    // The linear stages work per Fp2 COMPONENT (additions, halvings and negations are component-wise; xi mixes the two
+    // inputs but each output component is still one lane's job), and the workers are placed so that the long job sits
+    // alone in its warp: workers 0/1 (warps 0/1) own the e, f chain, workers 2/3, 6/7, 10/11 (warps 2/3) the rest.
+    if (tid < 10) {                                                        // m1, b, c, j, s from their Karatsuba parts
+        int w = tid >> 1, comp = tid & 1;
+        const Fp *p = &e.prod[3 * w];
+        T[2 * w + comp] = comp ? fp_sub(fp_sub(p[2], p[0]), p[1]) : fp_sub(p[0], p[1]);
     }
     __syncthreads();
-    if (tid == 0) {                                                        // g = (b + f) / 2
-        Fp g[2];
-        fp2s_add(g, &T[2], &T[12]); fp2s_half(&T[16], g);
-    } else if (tid == 1) {                                                 // co0 = i = e - b
-        Fp i[2];
-        fp2s_sub(i, &T[10], &T[2]);
-        m.co[0][0] = i[0]; m.co[0][1] = i[1];
-    } else if (tid == 2) {                                                 // b - f
-        fp2s_sub(&T[20], &T[2], &T[12]);
+    if (tid < 2) {                                                         // e = (4+4u)*3c = 4*xi*3c ; f = 3e
+        Fp d = tid ? fp_add(T[4], T[5]) : fp_sub(T[4], T[5]);              // (xi c).comp
+        Fp d3 = fp_add(fp_dbl(d), d);
+        Fp ee = fp_dbl(fp_dbl(d3));
+        T[10 + tid] = ee;
+        T[12 + tid] = fp_add(fp_dbl(ee), ee);
+    } else if (tid == 2 || tid == 3) {                                     // h = s - (b + c) ; co2 = -h
+        int comp = tid - 2;
+        Fp h = fp_sub(T[8 + comp], fp_add(T[2 + comp], T[4 + comp]));
+        T[18 + comp] = h;
+        m.co[2][comp] = fp_neg(h);
+    } else if (tid == 6 || tid == 7) {                                     // co1 = 3j
+        int comp = tid - 6;
+        Fp j = T[6 + comp];
+        m.co[1][comp] = fp_add(fp_dbl(j), j);
+    } else if (tid == 10 || tid == 11) {                                   // a = m1 / 2
+        int comp = tid - 10;
+        T[14 + comp] = fp_half(T[comp]);
+    }
+    __syncthreads();
+    if (tid < 2) {                                                         // g = (b + f) / 2
+        T[16 + tid] = fp_half(fp_add(T[2 + tid], T[12 + tid]));
+    } else if (tid == 2 || tid == 3) {                                     // co0 = i = e - b
+        int comp = tid - 2;
+        m.co[0][comp] = fp_sub(T[10 + comp], T[2 + comp]);
+    } else if (tid == 6 || tid == 7) {                                     // b - f
+        int comp = tid - 6;
+        T[20 + comp] = fp_sub(T[2 + comp], T[12 + comp]);
     }
     __syncthreads();
     // wave 2: 0: a*(b-f)  1: g^2  2: e^2  3: b*h
@@ -360,13 +399,19 @@ __device__ void miller_double(Engine &e, MillerState &m) {
         e.prod[tid] = fp2_part(part, A, B);
     }
     __syncthreads();
-    if (tid == 0) fp2_from_parts(m.rx, &e.prod[0]);
-    else if (tid == 1) fp2_from_parts(m.rz, &e.prod[9]);
-    else if (tid == 2) {
-        Fp g2[2], e2[2], t3[2];
-        fp2_from_parts(g2, &e.prod[3]); fp2_from_parts(e2, &e.prod[6]);
-        fp2s_add(t3, e2, e2); fp2s_add(t3, t3, e2);
-        fp2s_sub(m.ry, g2, t3);
+    if (tid < 2) {                                                         // ry = g^2 - 3 e^2, one component per worker
+        const Fp *pg = &e.prod[3], *pe = &e.prod[6];
+        Fp g2 = tid ? fp_sub(fp_sub(pg[2], pg[0]), pg[1]) : fp_sub(pg[0], pg[1]);
+        Fp e2 = tid ? fp_sub(fp_sub(pe[2], pe[0]), pe[1]) : fp_sub(pe[0], pe[1]);
+        m.ry[tid] = fp_sub(g2, fp_add(fp_dbl(e2), e2));
+    } else if (tid == 2 || tid == 3) {                                     // rx = a (b - f)
+        int comp = tid - 2;
+        const Fp *p = &e.prod[0];
+        m.rx[comp] = comp ? fp_sub(fp_sub(p[2], p[0]), p[1]) : fp_sub(p[0], p[1]);
+    } else if (tid == 6 || tid == 7) {                                     // rz = b h
+        int comp = tid - 6;
+        const Fp *p = &e.prod[9];
+        m.rz[comp] = comp ? fp_sub(fp_sub(p[2], p[0]), p[1]) : fp_sub(p[0], p[1]);
     }
     __syncthreads();
 }
