@@ -285,7 +285,7 @@ def run_ours(args, rank, world, local_rank):
 
     def time_host_calls(call, steps):
         """Wall clock around `steps` host C-ABI calls (each returns after its result is back in host memory)."""
-        for _ in range(2):
+        for _ in range(max(5, args.warmup)):          # also brings the PCIe link and the pinned-copy path out of idle
             call()
         torch.cuda.synchronize()
         t0 = time.perf_counter()
