@@ -257,9 +257,8 @@ def config_snarkpack(nproofs, with_cpu):
     m = n // 2
     while m >= 1:
         sizes = [2 * m, 2 * m, 2 * m, 2 * m, m, m]
-        t = time.perf_counter()
-        outs = lib.multi_pairing_batch(np.concatenate([a[:96 * k] for k in sizes]), np.concatenate([b[:192 * k] for k in sizes]), sizes)
-        g = time.perf_counter() - t
+        g1cat, g2cat = np.concatenate([a[:96 * k] for k in sizes]), np.concatenate([b[:192 * k] for k in sizes])
+        g, outs = timeit(lambda: lib.multi_pairing_batch(g1cat, g2cat, sizes))          # warm call first, then best of 3
         ent = {'m': m, 'pairs': sum(sizes), 'gpu_ms': g * 1e3}
         gpu_total += g
         pairs_total += sum(sizes)
