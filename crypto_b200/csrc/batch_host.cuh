@@ -184,12 +184,14 @@ static int32_t batch_mul_add_fixed(const uint8_t *points, const uint8_t *sa, uin
     const int glv = ctx().tunable[4].load() == 0 ? 1 : 0;
     // Below ~2^16 elements the call is latency-bound (one thread per element cannot fill the GPU): both products on one
     // doubling chain.  Larger batches are throughput-bound and the window table's 29 mixed additions per element are
-    // cheaper than 64 more full additions.  tunable 5: 1 forces the joint form, 2 the table form.
+    // cheaper than 64 more full additions.  tunable 5: 1 forces the joint form, 2 the table form, 3 the one-thread-per-element joint kernel.
     const int force = ctx().tunable[5].load();
-    const bool joint = v_affine || force == 1 || (force != 2 && m < 65536);
+    const bool joint = v_affine || force == 1 || force == 3 || (force != 2 && m < 65536);
     if (joint) {
         DG_LAUNCH(k_w4_table<F>, 1, 32, 0, t.stream, v_affine ? d_v : (const Affine<F> *)tb.dev + 1, d_vtbl);     // table[0][1] = V
-        DG_LAUNCH(k_batch_mul_add_joint<F>, div_up(m, 128), 128, 0, t.stream, d_p, d_sa, d_vtbl, d_sb, (uint32_t)m, d_o, glv);
+        // below ~2^14 elements even the joint form leaves most of the GPU idle: two threads per element, shorter chains
+        if (m < 16384 && force != 3) DG_LAUNCH(k_batch_mul_add_split<F>, div_up(m, 64), 128, 0, t.stream, d_p, d_sa, d_vtbl, d_sb, (uint32_t)m, d_o, glv);
+        else DG_LAUNCH(k_batch_mul_add_joint<F>, div_up(m, 128), 128, 0, t.stream, d_p, d_sa, d_vtbl, d_sb, (uint32_t)m, d_o, glv);
     } else {
         DG_LAUNCH(k_batch_mul_add_fixed<F>, div_up(m, 128), 128, 0, t.stream, d_p, d_sa, (const Affine<F> *)tb.dev, tb.window,
                   tb.nwin, d_sb, (uint32_t)m, d_o, glv);

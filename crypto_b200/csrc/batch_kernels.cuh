@@ -317,6 +317,33 @@ __global__ void __launch_bounds__(128) k_batch_mul_add_joint(const Affine<F> *__
     Affine<F> p = aff_load<F>(&points[i]);
     jac_store(&out[i], scalar_mul_w4(p, s, glv, vtbl, s2));
 }
+// Same result with TWO threads per element, for batches too small to fill the GPU with one thread each: warps 0-1 of a
+// CTA compute [a_i] P_i, warps 2-3 [b_i] V for the same 64 elements (each its own 128-doubling chain, 64 additions),
+// and the halves meet in shared memory for one final addition.  The chain per thread is a third shorter than the
+// joint one (128 dbl + 64 add instead of 128 + 128), which is what a latency-bound launch pays for.
+template <class F>
+__global__ void __launch_bounds__(128) k_batch_mul_add_split(const Affine<F> *__restrict__ points, const uint8_t *__restrict__ sa,
+                                                             const JacZ<F> *__restrict__ vtbl, const uint8_t *__restrict__ sb, uint32_t m,
+                                                             Jac<F> *__restrict__ out, int glv) {
+    __shared__ Jac<F> half[64];
+    const uint32_t role = threadIdx.x >> 6, slot = threadIdx.x & 63;          // role is warp-uniform
+    const uint32_t i = blockIdx.x * 64 + slot;
+    Jac<F> r = jac_inf<F>();
+    if (i < m) {
+        uint32_t s[9];
+        load_scalar(role ? sb : sa, i, s);
+        if (role == 0) {
+            Affine<F> p = aff_load<F>(&points[i]);
+            r = scalar_mul_w4(p, s, glv);
+        } else {
+            Affine<F> none = {fzero<F>(), fzero<F>()};                          // identity: only the V halves run
+            r = scalar_mul_w4(none, s, glv, vtbl, s);
+        }
+    }
+    if (role == 1) half[slot] = r;
+    __syncthreads();
+    if (role == 0 && i < m) jac_store(&out[i], jac_add_slow(r, half[slot]));
+}
 
 // ---- normalize_batch ---------------------------------------------------------------------------
 // Montgomery's trick on chunks of DG_NORM_CHUNK points per thread: one inversion per chunk.

@@ -250,14 +250,14 @@ def test_fused_witness_update(dg, cref):
     t = dg.FixedBaseTable(v, m)
     outs = []
     try:
-        for force in (1, 2):                       # joint doubling chain / window table
+        for force in (1, 3, 2):                    # two threads per element / one joint doubling chain / window table
             dg.dbg_set_tunable(5, force)
             outs.append(bytes(dg.batch_mul_add_fixed_g1(pts, sa, t, sb)))
     finally:
         dg.dbg_set_tunable(5, 0)
     t.free()
     outs.append(bytes(dg.batch_mul_add_same_g1(pts, sa, v, sb)))
-    assert outs[0] == outs[1] == outs[2]
+    assert outs[0] == outs[1] == outs[2] == outs[3]
     out = outs[0]
     # V = identity: only the a_i * C_i terms remain
     only_a = bytes(dg.batch_mul_add_same_g1(pts, sa, bytes(96), sb))
