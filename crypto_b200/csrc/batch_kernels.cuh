@@ -16,7 +16,7 @@ namespace dg {
 
 // ---- inversion -------------------------------------------------------------------------------
 // a^(p-2) by 4-bit fixed windows (381 squarings + ~95 multiplications); inv(0) = 0.
-static __device__ __noinline__ Fp fp_inv(const Fp &a) {
+static __device__ __noinline__ Fp fp_inv(Fp a) {
     Fp tbl[16];
     tbl[0] = fp_one();
     tbl[1] = a;
@@ -112,9 +112,10 @@ template <class F> __device__ __forceinline__ void scalar_mul_table(const Affine
     tbl[4] = jacz_of(p5); tbl[5] = jacz_of(p6); tbl[6] = jacz_of(p7); tbl[7] = jacz_of(p8);
 }
 // out-of-line group operations: one copy of each in the kernel instead of one per call site
-template <class F> static __device__ __noinline__ Jac<F> jac_dbl_ni(const Jac<F> &p) { return jac_dbl(p); }
-template <class F> static __device__ __noinline__ Jac<F> jac_add_z_ni(const Jac<F> &p, const JacZ<F> &q) { return jac_add_z(p, q); }
-template <class F> static __device__ __noinline__ void scalar_mul_table_ni(const Affine<F> &p, JacZ<F> *tbl) { scalar_mul_table(p, tbl); }
+// (operands copied into locals first: see fp_mul_ni in fp2.cuh)
+template <class F> static __device__ __noinline__ Jac<F> jac_dbl_ni(const Jac<F> &p_) { Jac<F> p = p_; return jac_dbl(p); }
+template <class F> static __device__ __noinline__ Jac<F> jac_add_z_ni(const Jac<F> &p_, const JacZ<F> &q_) { Jac<F> p = p_; JacZ<F> q = q_; return jac_add_z(p, q); }
+template <class F> static __device__ __noinline__ void scalar_mul_table_ni(const Affine<F> &p_, JacZ<F> *tbl) { Affine<F> p = p_; scalar_mul_table(p, tbl); }
 
 // [s] P (+ [s2] V) for 256-bit integers, signed 4-bit windows, uniform instruction stream.
 //   canonical scalars (< r), points in the prime-order subgroup -- what every reference call site passes

@@ -57,7 +57,8 @@ template <class F> __device__ __forceinline__ void jac_store(void *p, const Jac<
 
 // ---- XYZZ ----------------------------------------------------------------------------------
 // 2 * (affine point), mdbl-2008-s-1
-template <class F> __device__ __noinline__ XYZZ<F> xyzz_dbl_affine(const Affine<F> &p) {
+template <class F> __device__ __noinline__ XYZZ<F> xyzz_dbl_affine(const Affine<F> &p_) {
+    const Affine<F> p = p_;                                // local copy: see fp_mul_ni in fp2.cuh
     F u = fdbl(p.y), v = fsqr(u), w = fmul(u, v), s = fmul(p.x, v);
     F xx = fsqr(p.x), m = fadd(fdbl(xx), xx);
     XYZZ<F> r;
@@ -67,7 +68,8 @@ template <class F> __device__ __noinline__ XYZZ<F> xyzz_dbl_affine(const Affine<
     return r;
 }
 // 2 * (xyzz point), dbl-2008-s-1 (a = 0); caller guarantees p is not the identity
-template <class F> __device__ __noinline__ XYZZ<F> xyzz_dbl(const XYZZ<F> &p) {
+template <class F> __device__ __noinline__ XYZZ<F> xyzz_dbl(const XYZZ<F> &p_) {
+    const XYZZ<F> p = p_;
     F u = fdbl(p.y), v = fsqr(u), w = fmul(u, v), s = fmul(p.x, v);
     F xx = fsqr(p.x), m = fadd(fdbl(xx), xx);
     XYZZ<F> r;

@@ -22,7 +22,12 @@ template <> __device__ __forceinline__ Fp2 fone<Fp2>() { return {fp_one(), fp_ze
 
 // The Fp multiplier is ~400 SASS instructions; Fp2 and everything above it call it out of line
 // so G2 / pairing kernels stay inside the instruction cache.
-static __device__ __noinline__ Fp fp_mul_ni(const Fp &a, const Fp &b) { return fp_mul(a, b); }
+// The operands are passed BY VALUE (24 registers under the device ABI).  With `const Fp &` parameters the compiler must
+// assume they alias the returned object, re-reads the limbs from local memory between the asm statements of the
+// multiplier, and ptxas then no longer fuses the mad.lo.cc / madc.hi.cc pairs of the a * b rows into IMAD.WIDE:
+// 807 instead of ~500 instructions per call (ncu source counters of k_affine_round<Fp2>, profiles/ncu_affine_round_g2_r02.json).
+// Every out-of-line function below follows the same rule: operands by value or copied into locals first.
+static __device__ __noinline__ Fp fp_mul_ni(Fp a, Fp b) { return fp_mul(a, b); }
 
 __device__ __forceinline__ Fp2 fmul(const Fp2 &a, const Fp2 &b) {
     Fp t0 = fp_mul_ni(a.c0, b.c0);

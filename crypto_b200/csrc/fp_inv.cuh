@@ -49,7 +49,7 @@ __device__ __forceinline__ bool fp_raw_is_one(const Fp &a) {
     return t == 0;
 }
 
-static __device__ __noinline__ Fp fp_inv_binary(const Fp &a_mont) {
+static __device__ __noinline__ Fp fp_inv_binary(Fp a_mont) {
     if (fp_is_zero(a_mont)) return fp_zero();           // inv(0) = 0 like the Fermat version
     Fp u = a_mont, v, x1 = fp_zero(), x2 = fp_zero();
 #pragma unroll
@@ -94,7 +94,7 @@ __device__ __forceinline__ uint64_t fpi_take64(uint32_t h, uint32_t m, uint32_t 
     uint32_t lo = __funnelshift_r(l, m, s), hi = __funnelshift_r(m, h, s);
     return ((uint64_t)hi << 32) | lo;
 }
-static __device__ __noinline__ Fp fp_inv_pornin(const Fp &a_mont) {
+static __device__ __noinline__ Fp fp_inv_pornin(Fp a_mont) {
     uint32_t a[12], b[12], u[12], v[12];
 #pragma unroll
     for (int i = 0; i < 12; i++) { a[i] = a_mont.l[i]; b[i] = fp_p_limb(i); u[i] = 0; v[i] = 0; }

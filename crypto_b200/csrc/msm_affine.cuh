@@ -41,10 +41,10 @@ namespace dg {
 #define DG_BA_WARPS (DG_BA_THREADS / 32)
 
 // out-of-line multiplier for the once-per-batch phase 2 (keeps the kernel inside the instruction cache)
-static __device__ __noinline__ Fp ba_mul(const Fp &a, const Fp &b) { return fp_mul(a, b); }
-static __device__ __noinline__ Fp2 ba_mul(const Fp2 &a, const Fp2 &b) { return fmul(a, b); }
-static __device__ __noinline__ Fp ba_inv(const Fp &a) { return fp_inv_pornin(a); }
-static __device__ __noinline__ Fp2 ba_inv(const Fp2 &a) {
+static __device__ __noinline__ Fp ba_mul(Fp a, Fp b) { return fp_mul(a, b); }
+static __device__ __noinline__ Fp2 ba_mul(Fp2 a, Fp2 b) { return fmul(a, b); }
+static __device__ __noinline__ Fp ba_inv(Fp a) { return fp_inv_pornin(a); }
+static __device__ __noinline__ Fp2 ba_inv(Fp2 a) {
     Fp n = fp_add(fp_mul_ni(a.c0, a.c0), fp_mul_ni(a.c1, a.c1));
     Fp ni = fp_inv_pornin(n);
     return {fp_mul_ni(a.c0, ni), fp_neg(fp_mul_ni(a.c1, ni))};

@@ -12,7 +12,7 @@ static inline int ceil_log2_sz(size_t n) { int l = 0; while (((size_t)1 << l) < 
 // Window bits: about log2(n) - 4 so that an average bucket receives ~32 points per window,
 // which keeps the bucket reduction (2 * 2^(c-1) full additions per window) near 10 % of the
 // accumulation work.  nwin * c >= 256 so the top signed digit cannot overflow.
-static inline MsmGeom msm_geometry(size_t n, MsmPre pre) {
+static inline MsmGeom msm_geometry(size_t n, MsmPre pre, bool fp2 = false) {
     int c = pre.c ? pre.c : ctx().msm_window_override.load();
     const bool glv = !pre.c && ctx().tunable[4].load() == 0;
     if (c <= 0) {
@@ -39,7 +39,7 @@ static inline MsmGeom msm_geometry(size_t n, MsmPre pre) {
     g.nbw = 1u << (c - 1);
     g.nb = g.nbw * (uint32_t)g.nwin;
     g.row_stride = pre.c ? pre.row_stride : 0;
-    g.fp2 = 0;
+    g.fp2 = fp2 ? 1 : 0;
     g.phi_off = 0;
     return g;
 }
@@ -73,8 +73,7 @@ static inline int msm_affine_rounds(size_t n, const MsmGeom &g) {
 
 template <class F> static inline MsmLayout msm_layout(size_t n, MsmPre pre) {
     MsmLayout m;
-    m.g = msm_geometry(n, pre);
-    m.g.fp2 = sizeof(F) > 48;
+    m.g = msm_geometry(n, pre, sizeof(F) > 48);
     size_t max_entries = n * (size_t)m.g.ndig * (m.g.glv ? 2 : 1);
     m.R = msm_affine_rounds(n, m.g);
     m.mb[0] = max_entries;
@@ -160,7 +159,7 @@ static int32_t msm_run(const void *bases_dev, const void *scalars_dev, size_t n,
     }
     if (n >= (1ull << 31)) return fail(DG_ERR_BAD_ARG, "msm: n must be < 2^31");
     {
-        MsmGeom g0 = msm_geometry(n, pre);
+        MsmGeom g0 = msm_geometry(n, pre, sizeof(F) > 48);
         if ((uint64_t)n * g0.ndig * (g0.glv ? 2 : 1) >= 0xffffffffull)
             return fail(DG_ERR_BAD_ARG, "msm: n * digits must fit 32-bit entry offsets (n up to ~2^27)");
         if (g0.glv && (uint64_t)n + (pre.phi_off ? pre.phi_off : n) >= (1ull << 31))
@@ -272,8 +271,8 @@ static int32_t msm_run(const void *bases_dev, const void *scalars_dev, size_t n,
         if (!rc) rc = smem_opt_in(k_fixup_long_final<F>, smem_l);
         if (rc) return rc;
         XYZZ<F> *part = (XYZZ<F> *)(scratch + m.o_longpart);
-        DG_LAUNCH(k_fixup_long_part<F>, 4 * ctx().sm_count, 4 * QPL, smem_l, s, acc_off, m.L, head, tail, long_count, long_list, part);
-        DG_LAUNCH(k_fixup_long_final<F>, ctx().sm_count, 4 * QPL, smem_l, s, acc_off, m.L, buckets, long_count, long_list, part);
+        DG_LAUNCH(k_fixup_long_part<F>, 4 * ctx().sm_count, RedGeom<F>::THREADS, smem_l, s, acc_off, m.L, head, tail, long_count, long_list, part);
+        DG_LAUNCH(k_fixup_long_final<F>, ctx().sm_count, RedGeom<F>::THREADS, smem_l, s, acc_off, m.L, buckets, long_count, long_list, part);
     }
 
     // bucket reduction: line sums -> weighted subset sums -> window sums (three shallow stages, msm_kernels.cuh)
@@ -287,13 +286,20 @@ static int32_t msm_run(const void *bases_dev, const void *scalars_dev, size_t n,
         XYZZ<F> *lines = red[0], *vbuf = red[1], *ws_out = red[2];
         constexpr unsigned QP = RedGeom<F>::QP;
         const size_t smem = sizeof(QuadWS<F>) * QP;
-        int32_t rc = smem_opt_in(k_red_lines<F>, smem);
+        // G2: 12-lane quads for the line sums while every CTA is resident at once (the launch is latency-bound), 4-lane quads
+        // when the grid is several waves deep (tunable 6: 1 forces 4-lane, 2 forces 12-lane quads)
+        constexpr bool W = QuadWide<F>::value;
+        const int force_w = ctx().tunable[6].load();
+        const bool wide_lines = W && (force_w == 2 || (force_w != 1 && (size_t)nlines * g.nwin <= (size_t)ctx().sm_count * 4));
+        int32_t rc = smem_opt_in(k_red_lines<F, false>, smem);
+        if (!rc && W) rc = smem_opt_in(k_red_lines<F, W>, smem);
         if (!rc) rc = smem_opt_in(k_red_subsets<F>, smem);
         if (!rc) rc = smem_opt_in(k_red_final<F>, smem);
         if (rc) return rc;
-        DG_LAUNCH(k_red_lines<F>, dim3(nlines, g.nwin), 4 * QP, smem, s, buckets, g.nbw, LO, HI, lines, m.red_stride);
-        DG_LAUNCH(k_red_subsets<F>, dim3(nv, g.nwin), 4 * QP, smem, s, lines, m.red_stride, LO, HI, vbuf, 32u);
-        DG_LAUNCH(k_red_final<F>, dim3(1, g.nwin), 4 * QP, smem, s, vbuf, 32u, (int)nv, ws_out, 1u);
+        if (wide_lines) DG_LAUNCH((k_red_lines<F, W>), dim3(nlines, g.nwin), RedGeom<F>::threads(W), smem, s, buckets, g.nbw, LO, HI, lines, m.red_stride);
+        else DG_LAUNCH((k_red_lines<F, false>), dim3(nlines, g.nwin), RedGeom<F>::threads(false), smem, s, buckets, g.nbw, LO, HI, lines, m.red_stride);
+        DG_LAUNCH(k_red_subsets<F>, dim3(nv, g.nwin), RedGeom<F>::THREADS, smem, s, lines, m.red_stride, LO, HI, vbuf, 32u);
+        DG_LAUNCH(k_red_final<F>, dim3(1, g.nwin), RedGeom<F>::THREADS, smem, s, vbuf, 32u, (int)nv, ws_out, 1u);
         wsum = ws_out;
         wsum_stride = 1;
     }

@@ -331,25 +331,31 @@ __global__ void __launch_bounds__(128) k_bucket_fixup(const uint32_t *__restrict
 // the dependent-operation depth is ~ len/QP + log2 QP per stage (three stages + j doublings) instead of
 // the 27 operations per level x 5..6 levels of a multi-level running-sum scheme (measured 0.69 ms at
 // N = 2^15, all of it latency; this scheme 0.24 ms).
-template <class F> struct RedGeom { static constexpr int QP = sizeof(F) > 48 ? 16 : 32; };   // quads per CTA (48 KB of workspace)
+template <class F> struct RedGeom {
+    static constexpr int QP = sizeof(F) > 48 ? 16 : 32;                     // quads per CTA (48 KB of workspace)
+    static constexpr int threads(bool wide) { return wide ? QuadLanes<true>::cta_threads(QP) : QuadLanes<false>::cta_threads(QP); }
+    static constexpr int THREADS = threads(QuadWide<F>::value);             // 128 (G1: 4 lanes per quad), 256 (G2: 12 lanes per quad)
+};
 
 // quad-cooperative: ACC of quad `qi` := sum of the items item(k), k in [0, count) (skipping k with bit `bit` clear when
 // bit >= 0); the total is valid in quad 0 after the shared-memory tree.
 template <class F, class ItemFn>
 __device__ __forceinline__ void red_cta_sum_fn(QuadWS<F> *wsall, uint32_t count, int bit, ItemFn item, const QuadCtx &qc) {
     constexpr int QP = RedGeom<F>::QP;
-    const uint32_t qi = threadIdx.x >> 2;
+    const uint32_t qi = qc.qi;
     QuadWS<F> &ws = wsall[qi];
     enum { ACC = 1, ITEM = 2 };
-    quad_set_inf(ws, ACC, qc);
-    for (uint32_t k = qi; k < count; k += QP) {
-        if (bit >= 0 && !((k >> bit) & 1u)) continue;                     // quad-uniform
-        quad_load(ws, ITEM, item(k), qc);
-        quad_add(ws, ACC, ACC, ITEM, qc);
+    if (qc.active) {
+        quad_set_inf(ws, ACC, qc);
+        for (uint32_t k = qi; k < count; k += QP) {
+            if (bit >= 0 && !((k >> bit) & 1u)) continue;                 // quad-uniform
+            quad_load(ws, ITEM, item(k), qc);
+            quad_add(ws, ACC, ACC, ITEM, qc);
+        }
     }
     __syncthreads();
     for (uint32_t s = QP / 2; s > 0; s >>= 1) {
-        if (qi < s) {
+        if (qc.active && qi < s) {
             quad_load(ws, ITEM, reinterpret_cast<const XYZZ<F> *>(&wsall[qi + s].v[4 * ACC]), qc);
             quad_add(ws, ACC, ACC, ITEM, qc);
         }
@@ -372,13 +378,13 @@ template <class F> __device__ __forceinline__ uint32_t long_split(uint32_t np) {
     return s > DG_LONG_SPLIT ? DG_LONG_SPLIT : (s ? s : 1);
 }
 template <class F>
-__global__ void __launch_bounds__(4 * RedGeom<F>::QP) k_fixup_long_part(const uint32_t *__restrict__ off, uint32_t L,
+__global__ void __launch_bounds__(RedGeom<F>::THREADS) k_fixup_long_part(const uint32_t *__restrict__ off, uint32_t L,
                                                                          const XYZZ<F> *__restrict__ head, const XYZZ<F> *__restrict__ tail,
                                                                          const uint32_t *__restrict__ long_count,
                                                                          const uint32_t *__restrict__ long_list, XYZZ<F> *__restrict__ part) {
     extern __shared__ __align__(16) unsigned char dg_smem_quad[];
     QuadWS<F> *wsall = reinterpret_cast<QuadWS<F> *>(dg_smem_quad);
-    QuadCtx qc = quad_ctx();
+    QuadCtx qc = quad_ctx<QuadWide<F>::value>();
     const uint32_t cnt = *long_count;
     for (uint32_t idx = blockIdx.x; idx < cnt * DG_LONG_SPLIT; idx += gridDim.x) {       // CTA-uniform loop
         const uint32_t i = idx / DG_LONG_SPLIT, si = idx % DG_LONG_SPLIT;
@@ -393,56 +399,56 @@ __global__ void __launch_bounds__(4 * RedGeom<F>::QP) k_fixup_long_part(const ui
             const uint32_t j = lo + k;
             return (j == 0 && !first0) ? &tail[t0] : &head[t0 + j];
         }, qc);
-        if ((threadIdx.x >> 2) == 0) quad_store(wsall[0], 1, &part[(size_t)i * DG_LONG_SPLIT + si], qc);
+        if (qc.active && qc.qi == 0) quad_store(wsall[0], 1, &part[(size_t)i * DG_LONG_SPLIT + si], qc);
         __syncthreads();                                                                  // workspace is reused by the next item
     }
 }
 template <class F>
-__global__ void __launch_bounds__(4 * RedGeom<F>::QP) k_fixup_long_final(const uint32_t *__restrict__ off, uint32_t L,
+__global__ void __launch_bounds__(RedGeom<F>::THREADS) k_fixup_long_final(const uint32_t *__restrict__ off, uint32_t L,
                                                                           XYZZ<F> *__restrict__ buckets, const uint32_t *__restrict__ long_count,
                                                                           const uint32_t *__restrict__ long_list, const XYZZ<F> *__restrict__ part) {
     extern __shared__ __align__(16) unsigned char dg_smem_quad[];
     QuadWS<F> *wsall = reinterpret_cast<QuadWS<F> *>(dg_smem_quad);
-    QuadCtx qc = quad_ctx();
+    QuadCtx qc = quad_ctx<QuadWide<F>::value>();
     const uint32_t cnt = *long_count;
     for (uint32_t i = blockIdx.x; i < cnt; i += gridDim.x) {
         const uint32_t b = long_list[i];
         const uint32_t s = off[b], e = off[b + 1];
         const uint32_t np = (e - 1) / L - s / L + 1;
         red_cta_sum<F>(wsall, part + (size_t)i * DG_LONG_SPLIT, long_split<F>(np), 1, -1, qc);
-        if ((threadIdx.x >> 2) == 0) quad_store(wsall[0], 1, &buckets[b], qc);
+        if (qc.active && qc.qi == 0) quad_store(wsall[0], 1, &buckets[b], qc);
         __syncthreads();
     }
 }
 
 // stage A: line sums.  grid (2^HI rows + 2^LO columns, nwin); lines[w][0 .. 2^HI) = R, lines[w][2^HI ..) = C
-template <class F>
-__global__ void __launch_bounds__(4 * RedGeom<F>::QP) k_red_lines(const XYZZ<F> *__restrict__ buckets, uint32_t nbw, int LO, int HI,
+template <class F, bool WIDE>
+__global__ void __launch_bounds__(RedGeom<F>::threads(WIDE)) k_red_lines(const XYZZ<F> *__restrict__ buckets, uint32_t nbw, int LO, int HI,
                                                                    XYZZ<F> *__restrict__ lines, uint32_t line_stride) {
     extern __shared__ __align__(16) unsigned char dg_smem_quad[];
     QuadWS<F> *wsall = reinterpret_cast<QuadWS<F> *>(dg_smem_quad);
-    QuadCtx qc = quad_ctx();
+    QuadCtx qc = quad_ctx<WIDE>();
     const uint32_t w = blockIdx.y, line = blockIdx.x, nrows = 1u << HI, ncols = 1u << LO;
     const XYZZ<F> *bw = buckets + (size_t)w * nbw;
     if (line < nrows) red_cta_sum<F>(wsall, bw + (size_t)line * ncols, ncols, 1, -1, qc);            // row h: contiguous
     else red_cta_sum<F>(wsall, bw + (line - nrows), nrows, ncols, -1, qc);                            // column l: stride 2^LO
-    if ((threadIdx.x >> 2) == 0) quad_store(wsall[0], 1, &lines[(size_t)w * line_stride + line], qc);
+    if (qc.active && qc.qi == 0) quad_store(wsall[0], 1, &lines[(size_t)w * line_stride + line], qc);
 }
 
 // stage B: V_j = 2^j U_j for j < LO + HI, V_{LO+HI} = T.  grid (LO + HI + 1, nwin)
 template <class F>
-__global__ void __launch_bounds__(4 * RedGeom<F>::QP) k_red_subsets(const XYZZ<F> *__restrict__ lines, uint32_t line_stride, int LO, int HI,
+__global__ void __launch_bounds__(RedGeom<F>::THREADS) k_red_subsets(const XYZZ<F> *__restrict__ lines, uint32_t line_stride, int LO, int HI,
                                                                      XYZZ<F> *__restrict__ vout, uint32_t v_stride) {
     extern __shared__ __align__(16) unsigned char dg_smem_quad[];
     QuadWS<F> *wsall = reinterpret_cast<QuadWS<F> *>(dg_smem_quad);
-    QuadCtx qc = quad_ctx();
+    QuadCtx qc = quad_ctx<QuadWide<F>::value>();
     const uint32_t w = blockIdx.y, nrows = 1u << HI, ncols = 1u << LO;
     const int j = (int)blockIdx.x;
     const XYZZ<F> *R = lines + (size_t)w * line_stride, *Cc = R + nrows;
     if (j < LO) red_cta_sum<F>(wsall, Cc, ncols, 1, j, qc);
     else if (j < LO + HI) red_cta_sum<F>(wsall, R, nrows, 1, j - LO, qc);
     else red_cta_sum<F>(wsall, R, nrows, 1, -1, qc);
-    if ((threadIdx.x >> 2) == 0) {
+    if (qc.active && qc.qi == 0) {
         QuadWS<F> &ws = wsall[0];
         if (j < LO + HI)
             for (int k = 0; k < j; k++)
@@ -453,14 +459,14 @@ __global__ void __launch_bounds__(4 * RedGeom<F>::QP) k_red_subsets(const XYZZ<F
 
 // stage C: S_w = sum_j V_j.  grid (1, nwin)
 template <class F>
-__global__ void __launch_bounds__(4 * RedGeom<F>::QP) k_red_final(const XYZZ<F> *__restrict__ v, uint32_t v_stride, int nv,
+__global__ void __launch_bounds__(RedGeom<F>::THREADS) k_red_final(const XYZZ<F> *__restrict__ v, uint32_t v_stride, int nv,
                                                                    XYZZ<F> *__restrict__ wsum, uint32_t wsum_stride) {
     extern __shared__ __align__(16) unsigned char dg_smem_quad[];
     QuadWS<F> *wsall = reinterpret_cast<QuadWS<F> *>(dg_smem_quad);
-    QuadCtx qc = quad_ctx();
+    QuadCtx qc = quad_ctx<QuadWide<F>::value>();
     const uint32_t w = blockIdx.y;
     red_cta_sum<F>(wsall, v + (size_t)w * v_stride, (uint32_t)nv, 1, -1, qc);
-    if ((threadIdx.x >> 2) == 0) quad_store(wsall[0], 1, &wsum[(size_t)w * wsum_stride], qc);
+    if (qc.active && qc.qi == 0) quad_store(wsall[0], 1, &wsum[(size_t)w * wsum_stride], qc);
 }
 
 // window sums S_w (one XYZZ per window at stride) -> sum_w 2^(c w) S_w, Horner from the top,
@@ -469,8 +475,8 @@ template <class F>
 __global__ void __launch_bounds__(32) k_window_combine(const XYZZ<F> *__restrict__ wsum, uint32_t stride, int nwin, int c, Jac<F> *out) {
     extern __shared__ __align__(16) unsigned char dg_smem_quad[];
     QuadWS<F> &ws = reinterpret_cast<QuadWS<F> *>(dg_smem_quad)[0];
-    if (threadIdx.x >= 4 || blockIdx.x != 0) return;
-    QuadCtx qc = quad_ctx();
+    QuadCtx qc = quad_ctx<QuadWide<F>::value>();
+    if (!qc.active || qc.qi != 0 || blockIdx.x != 0) return;
     enum { ACC = 1, ITEM = 2 };
     quad_load(ws, ACC, &wsum[(size_t)(nwin - 1) * stride], qc);
     for (int w = nwin - 2; w >= 0; w--) {
@@ -479,6 +485,7 @@ __global__ void __launch_bounds__(32) k_window_combine(const XYZZ<F> *__restrict
         quad_load(ws, ITEM, &wsum[(size_t)w * stride], qc);
         quad_add(ws, ACC, ACC, ITEM, qc);
     }
+    __syncwarp(qc.mask);
     if (threadIdx.x == 0) {
         XYZZ<F> r = {ws.v[4 * ACC], ws.v[4 * ACC + 1], ws.v[4 * ACC + 2], ws.v[4 * ACC + 3]};
         jac_store(out, xyzz_to_jac(r));

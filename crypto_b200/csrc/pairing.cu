@@ -38,7 +38,9 @@ __device__ __forceinline__ int pair_wid() { return (int)((threadIdx.x & 31u) * 4
 struct F12 { Fp c[12]; };
 __device__ __forceinline__ int widx(int k) { return (k & 1) * 6 + (k >> 1) * 2; }
 
-static __device__ __noinline__ Fp fp_mul_smem(const Fp *a, const Fp *b) { return fp_mul(*a, *b); }
+// operands by value: see fp_mul_ni in fp2.cuh (with pointer parameters the a * b rows are not fused into IMAD.WIDE)
+static __device__ __noinline__ Fp fp_mul_val(Fp a, Fp b) { return fp_mul(a, b); }
+static __device__ __forceinline__ Fp fp_mul_smem(const Fp *a, const Fp *b) { return fp_mul_val(*a, *b); }
 
 // One Karatsuba part of an Fp2 product: 0: a0*b0, 1: a1*b1, 2: (a0+a1)*(b0+b1)
 // ONE call site for the multiplier: with three calls in three branches the lanes of a warp holding parts 0, 1 and 2
@@ -231,7 +233,7 @@ __device__ void f12_frobenius(Engine &e, F12 *d, const F12 *s, int pw) {
 }
 
 // Fp inversion by one thread (a^(p-2)); the only long serial chain in the final exponentiation
-static __device__ __noinline__ Fp fp_inv_serial(const Fp &a) {
+static __device__ __noinline__ Fp fp_inv_serial(Fp a) {
     Fp tbl[16];
     tbl[0] = fp_one();
     tbl[1] = a;
@@ -266,9 +268,9 @@ __device__ void f12_inv(Engine &e, F12 *d, const F12 *s, F12 *t0, F12 *t1, F12 *
     f12_mul(e, t1, t1, d);           // Norm in Fp2: only the w^0 coefficient is non-zero
     if (tid == 0) {
         Fp x = t1->c[0], y = t1->c[1];
-        Fp n = fp_inv_pornin(fp_add(fp_mul(x, x), fp_mul(y, y)));
-        t1->c[0] = fp_mul(x, n);
-        t1->c[1] = fp_neg(fp_mul(y, n));
+        Fp n = fp_inv_pornin(fp_add(fp_mul_val(x, x), fp_mul_val(y, y)));
+        t1->c[0] = fp_mul_val(x, n);
+        t1->c[1] = fp_neg(fp_mul_val(y, n));
     }
     __syncthreads();
     f12_mul(e, d, t0, t1);
@@ -506,8 +508,10 @@ __device__ void miller_ell(Engine &e, MillerState &m, F12 *f) {
     if (tid < 12) m.line.c[tid] = fp_zero();
     __syncthreads();
     if (tid < 2) m.line.c[widx(0) + tid] = m.co[0][tid];
-    else if (tid < 4) m.line.c[widx(2) + (tid - 2)] = fp_mul(m.co[1][tid - 2], m.px);
-    else if (tid < 6) m.line.c[widx(3) + (tid - 4)] = fp_mul(m.co[2][tid - 4], m.py);
+    else if (tid < 6) {                                              // one call site: the four products run together
+        const int j = (tid - 2) & 1, hi = tid >= 4;
+        m.line.c[widx(hi ? 3 : 2) + j] = fp_mul_val(hi ? m.co[2][j] : m.co[1][j], hi ? m.py : m.px);
+    }
     __syncthreads();
     f12_mul(e, f, f, &m.line);
 }

@@ -7,6 +7,13 @@
 // one product per lane, with operands and results exchanged through a per-quad shared-memory
 // workspace.  All lanes run the same instruction stream (operands are selected by pointer), so a
 // warp of 8 quads never diverges on the common path.
+//
+// Over Fp2 (G2) one product is three Fp multiplications (Karatsuba), which one lane would run back to back, so there a
+// "quad" is 12 lanes: each of the four quad members is a trio of adjacent lanes holding the same operands, trio lane k
+// multiplies Karatsuba part k (a0 b0, a1 b1, (a0 + a1)(b0 + b1)) and the three products are exchanged by shuffles.
+// A wave then costs one Fp multiplication plus ~36 shuffles instead of three multiplications and the call overhead
+// (measured on B200, G2 MSM at 2^18 terms: window combination 1.89 -> see DESIGN.md section 3).  Two such quads fit a warp;
+// lanes 24..31 idle.
 #pragma once
 #include "ec.cuh"
 
@@ -18,15 +25,65 @@ namespace dg {
 template <class F> struct QuadWS { F v[DG_Q_TMP + 16]; };
 
 struct QuadCtx {
-    uint32_t ql;        // lane within the quad, 0..3
-    uint32_t mask;      // __syncwarp mask of this quad
+    uint32_t ql;        // member within the quad, 0..3
+    uint32_t mask;      // __syncwarp / __shfl_sync mask of this quad
+    uint32_t part;      // Fp2: Karatsuba part of this lane within its trio (0..2); Fp: 0
+    uint32_t base;      // Fp2: first lane of this lane's trio
+    uint32_t qi;        // index of the quad within the CTA
+    bool active;        // false for the warp's left-over lanes (Fp2: lanes 24..31): they only take part in CTA barriers
+    bool wide;          // 12-lane quads (Fp2 only)
 };
-__device__ __forceinline__ QuadCtx quad_ctx() {
-    uint32_t lane = threadIdx.x & 31;
+// WIDE = 12 lanes per quad.  It pays where a launch is latency-bound (few CTAs, long dependent chains); a launch that
+// fills the GPU with CTAs is better off with 4-lane quads (no idle lanes, no redundant linear work in the trios).
+template <class F> struct QuadWide { static constexpr bool value = sizeof(F) > 48; };
+template <bool WIDE> struct QuadLanes {
+    static constexpr int LPQ = WIDE ? 12 : 4;                 // lanes per quad
+    static constexpr int QPW = 32 / LPQ;                      // quads per warp
+    static constexpr int cta_threads(int quads) { return (quads + QPW - 1) / QPW * 32; }
+};
+template <bool WIDE> __device__ __forceinline__ QuadCtx quad_ctx() {
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     QuadCtx q;
-    q.ql = lane & 3;
-    q.mask = 0xFu << (lane & ~3u);
+    q.wide = WIDE;
+    if (WIDE) {
+        const uint32_t qw = lane / 12, l12 = lane - 12 * qw;
+        q.ql = l12 / 3;
+        q.part = l12 - 3 * q.ql;
+        q.base = 12 * qw + 3 * q.ql;
+        q.active = qw < 2;
+        q.mask = q.active ? (0xFFFu << (12 * qw)) : 0xFF000000u;
+        q.qi = warp * 2 + (q.active ? qw : 0);
+    } else {
+        q.ql = lane & 3;
+        q.part = 0;
+        q.base = lane;
+        q.active = true;
+        q.mask = 0xFu << (lane & ~3u);
+        q.qi = threadIdx.x >> 2;
+    }
     return q;
+}
+
+// one product per quad member: plain for Fp, split over the member's trio for Fp2 (all 12 lanes of the quad call this
+// together; the operands are identical in the three lanes of a trio)
+__device__ __forceinline__ Fp qmul(const Fp &a, const Fp &b, const QuadCtx &) { return fmul(a, b); }
+__device__ __forceinline__ Fp2 qmul(const Fp2 &a, const Fp2 &b, const QuadCtx &q) {
+    if (!q.wide) return fmul(a, b);
+    Fp x = fsel(q.part == 0, a.c0, a.c1), y = fsel(q.part == 0, b.c0, b.c1);
+    Fp xs = fp_add(a.c0, a.c1), ys = fp_add(b.c0, b.c1);
+    x = fsel(q.part == 2, xs, x);
+    y = fsel(q.part == 2, ys, y);
+    Fp t = fp_mul_ni(x, y), t0, t1, t2;
+#pragma unroll
+    for (int i = 0; i < 12; i++) {
+        t0.l[i] = __shfl_sync(q.mask, t.l[i], q.base);
+        t1.l[i] = __shfl_sync(q.mask, t.l[i], q.base + 1);
+        t2.l[i] = __shfl_sync(q.mask, t.l[i], q.base + 2);
+    }
+    Fp2 r;
+    r.c0 = fp_sub(t0, t1);
+    r.c1 = fp_sub(fp_sub(t2, t0), t1);
+    return r;
 }
 
 template <class F> __device__ __forceinline__ void quad_set_inf(QuadWS<F> &w, int D, const QuadCtx &q) {
@@ -38,7 +95,7 @@ template <class F> __device__ __forceinline__ void quad_load(QuadWS<F> &w, int D
     __syncwarp(q.mask);
 }
 template <class F> __device__ __forceinline__ void quad_store(const QuadWS<F> &w, int S, XYZZ<F> *dst, const QuadCtx &q) {
-    fstore(reinterpret_cast<char *>(dst) + q.ql * sizeof(F), w.v[4 * S + q.ql]);
+    if (q.part == 0) fstore(reinterpret_cast<char *>(dst) + q.ql * sizeof(F), w.v[4 * S + q.ql]);
 }
 
 // D = 2 * A (dbl-2008-s-1, a = 0); A must not be the identity.  D may alias A.
@@ -49,7 +106,7 @@ template <class F> __device__ __noinline__ void quad_dbl(QuadWS<F> &w, int D, in
     F a, b, r;
     // wave 1: V = (2Y)^2 (even lanes), XX = X^2 (odd lanes)
     if (q.ql & 1) a = PA[0]; else a = fdbl(PA[1]);
-    r = fmul(a, a);
+    r = qmul(a, a, q);
     if (q.ql < 2) T[q.ql] = r;                             // T0 = V, T1 = XX
     if (q.ql == 2) T[2] = a;                               // T2 = U = 2Y
     __syncwarp(q.mask);
@@ -61,7 +118,7 @@ template <class F> __device__ __noinline__ void quad_dbl(QuadWS<F> &w, int D, in
         case 2: a = M; b = M; break;
         default: a = T[0]; b = PA[2]; break;
     }
-    r = fmul(a, b);
+    r = qmul(a, b, q);
     T[3 + q.ql] = r;                                       // T3 = W, T4 = S, T5 = MM, T6 = ZZ3
     __syncwarp(q.mask);
     F X3 = fsub(T[5], fdbl(T[4]));
@@ -71,7 +128,7 @@ template <class F> __device__ __noinline__ void quad_dbl(QuadWS<F> &w, int D, in
         case 1: a = T[3]; b = PA[1]; break;
         default: a = T[3]; b = PA[3]; break;
     }
-    r = fmul(a, b);
+    r = qmul(a, b, q);
     if (q.ql < 3) T[7 + q.ql] = r;                         // T7, T8, T9 = ZZZ3
     __syncwarp(q.mask);
     F out;
@@ -106,7 +163,7 @@ template <class F> __device__ __noinline__ void quad_add(QuadWS<F> &w, int D, in
         case 2: a = PA[1]; b = PB[3]; break;
         default: a = PB[1]; b = PA[3]; break;
     }
-    T[q.ql] = fmul(a, b);
+    T[q.ql] = qmul(a, b, q);
     __syncwarp(q.mask);
     F P = fsub(T[1], T[0]), R = fsub(T[3], T[2]);
     if (fis_zero(P)) {                                     // quad-uniform, rare
@@ -127,7 +184,7 @@ template <class F> __device__ __noinline__ void quad_add(QuadWS<F> &w, int D, in
         case 2: a = PA[2]; b = PB[2]; break;
         default: a = PA[3]; b = PB[3]; break;
     }
-    T[4 + q.ql] = fmul(a, b);
+    T[4 + q.ql] = qmul(a, b, q);
     __syncwarp(q.mask);
     // wave 3: PPP = P*PP, Q = U1*PP, ZZ3 = ZZ12*PP
     switch (q.ql) {
@@ -135,7 +192,7 @@ template <class F> __device__ __noinline__ void quad_add(QuadWS<F> &w, int D, in
         case 1: a = T[0]; break;
         default: a = T[6]; break;
     }
-    r = fmul(a, T[4]);
+    r = qmul(a, T[4], q);
     if (q.ql < 3) T[8 + q.ql] = r;                         // T8 = PPP, T9 = Q, T10 = ZZ3
     __syncwarp(q.mask);
     F X3 = fsub(fsub(T[5], T[8]), fdbl(T[9]));
@@ -145,7 +202,7 @@ template <class F> __device__ __noinline__ void quad_add(QuadWS<F> &w, int D, in
         case 1: a = T[2]; b = T[8]; break;
         default: a = T[7]; b = T[8]; break;
     }
-    r = fmul(a, b);
+    r = qmul(a, b, q);
     if (q.ql < 3) T[11 + q.ql] = r;                        // T11, T12, T13 = ZZZ3
     __syncwarp(q.mask);
     F out;

@@ -35,7 +35,7 @@ __device__ __forceinline__ Fp fp_const(const uint32_t *c) {
     for (int i = 0; i < 12; i++) r.l[i] = c[i];
     return r;
 }
-static __device__ __noinline__ Fp sfp_mul(const Fp &a, const Fp &b) { return fp_mul(a, b); }
+static __device__ __noinline__ Fp sfp_mul(Fp a, Fp b) { return fp_mul(a, b); }     // by value: see fp_mul_ni in fp2.cuh
 __device__ __forceinline__ Fp fp_to_mont(const Fp &raw) { return sfp_mul(raw, fp_const(DGC_R2)); }
 __device__ __forceinline__ Fp fp_from_mont(const Fp &m) {
     Fp one = fp_zero();
@@ -90,7 +90,8 @@ __device__ __forceinline__ bool lex_largest(const Fp &y) { return fp_lex_largest
 __device__ __forceinline__ bool lex_largest(const Fp2 &y) { return fp_is_zero(y.c1) ? fp_lex_largest(y.c0) : fp_lex_largest(y.c1); }
 
 // [k] P for a 128-bit k, left-to-right double-and-add with mixed additions
-template <class F> static __device__ __noinline__ Jac<F> jac_mul_u128(const Affine<F> &p, uint64_t hi, uint64_t lo) {
+template <class F> static __device__ __noinline__ Jac<F> jac_mul_u128(const Affine<F> &p_, uint64_t hi, uint64_t lo) {
+    const Affine<F> p = p_;                              // local copy: see fp_mul_ni in fp2.cuh
     Jac<F> acc = jac_inf<F>();
     bool started = false;
     for (int bit = 127; bit >= 0; bit--) {

@@ -1,4 +1,5 @@
-"""Run a G2 MSM twice after warm-up (for ncu): python tools/msm_run_g2.py LOGN C   (C = 0: plain handle, else table window)"""
+"""Run a G2 MSM twice after warm-up (for ncu): python tools/msm_run_g2.py LOGN C [W]
+(C = 0: plain handle, else table window; W: bucket window override for the plain handle)"""
 import sys, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
@@ -15,6 +16,8 @@ hb = lib.Bases(bases, g2=True)
 if c:
     hb.precompute(c)
 d_s = torch.from_numpy(np.array(sc)).cuda(); d_o = torch.zeros(288, dtype=torch.uint8, device='cuda')
+if len(sys.argv) > 3:
+    lib.msm_set_window(int(sys.argv[3]))
 ts = torch.cuda.Stream(); torch.cuda.set_stream(ts)
 for _ in range(2):
     lib.msm_handle_device(hb, d_s.data_ptr(), n, d_o.data_ptr(), ts.cuda_stream)
