@@ -198,7 +198,120 @@ __device__ __forceinline__ Fp fp_mul(const Fp &a, const Fp &b) {
     return r;
 }
 
-__device__ __forceinline__ Fp fp_sqr(const Fp &a) { return fp_mul(a, a); }
+// ---- dedicated squaring ----------------------------------------------------------------------
+// a^2 = sum_i a_i^2 2^(64 i) + 2 sum_{i<j} a_i a_j 2^(32 (i + j)): 66 cross products + 12 squares instead of 144 products,
+// then the 12 reduction rows of the multiplier on the low half of the 24-limb square and one addition of the high half.
+// 222 wide multiply-adds against 288 for fp_mul(a, a).  The cross products keep the even/odd split: column i + j even goes
+// to A (A[k] = column k), odd to O (O[k] = column k + 1), so every product is one IMAD.WIDE on an aligned register pair and
+// each row is two unbroken carry chains whose carry-out falls into a limb no earlier row has touched.
+//
+// acc'[j] = acc[j + 2] + {p[1], p[3], ..} * m with carry-in from CC: the reduction row's half that also absorbs the shift
+__device__ __forceinline__ void dg_madc_row_rshift_p(uint32_t *acc, uint32_t m) {
+#pragma unroll
+    for (int j = 0; j < 10; j += 2) {
+        asm volatile("madc.lo.cc.u32 %0, %1, %2, %3;" : "=r"(acc[j]) : "r"(m), "r"(fp_p_limb(1 + j)), "r"(acc[j + 2]));
+        asm volatile("madc.hi.cc.u32 %0, %1, %2, %3;" : "=r"(acc[j + 1]) : "r"(m), "r"(fp_p_limb(1 + j)), "r"(acc[j + 3]));
+    }
+    asm volatile("madc.lo.cc.u32 %0, %1, %2, 0;" : "=r"(acc[10]) : "r"(m), "r"(fp_p_limb(11)));
+    asm volatile("madc.hi.u32 %0, %1, %2, 0;" : "=r"(acc[11]) : "r"(m), "r"(fp_p_limb(11)));
+}
+// one Montgomery reduction row without a product row: (al, of) as in dg_mont_row<false>
+__device__ __forceinline__ void dg_redc_row(uint32_t *al, uint32_t *of) {
+    const uint32_t m = (al[0] + of[1]) * DG_FP_INV32;
+    asm volatile("add.cc.u32 %0, %0, %1;" : "+r"(al[0]) : "r"(of[1]));   // carry -> column 1
+    dg_madc_row_rshift_p(of, m);                                           // columns 1..12
+    dg_cmad_row_p<0>(al, m);                                               // columns 0..11
+    asm volatile("addc.u32 %0, %0, 0;" : "+r"(of[11]));                    // column 12
+}
+
+__device__ __forceinline__ Fp fp_sqr(const Fp &x) {
+#ifdef DG_FP_SQR_VIA_MUL
+    return fp_mul(x, x);
+#else
+    const uint32_t *a = x.l;
+    uint32_t A[24], O[24];
+    // row 0 initialises O[0..11] and A[2..11]
+#pragma unroll
+    for (int j = 1; j < 12; j += 2) {
+        asm volatile("mul.lo.u32 %0, %1, %2;" : "=r"(O[j - 1]) : "r"(a[0]), "r"(a[j]));
+        asm volatile("mul.hi.u32 %0, %1, %2;" : "=r"(O[j]) : "r"(a[0]), "r"(a[j]));
+    }
+#pragma unroll
+    for (int j = 2; j < 12; j += 2) {
+        asm volatile("mul.lo.u32 %0, %1, %2;" : "=r"(A[j]) : "r"(a[0]), "r"(a[j]));
+        asm volatile("mul.hi.u32 %0, %1, %2;" : "=r"(A[j + 1]) : "r"(a[0]), "r"(a[j]));
+    }
+#pragma unroll
+    for (int k = 12; k < 24; k++) { A[k] = 0; O[k] = 0; }
+#pragma unroll
+    for (int i = 1; i < 11; i++) {
+        {   // i + j odd -> O[i + j - 1], O[i + j]
+            int last = 0;
+#pragma unroll
+            for (int j = i + 1; j < 12; j += 2) {
+                const int k = i + j - 1;
+                if (j == i + 1) asm volatile("mad.lo.cc.u32 %0, %1, %2, %0;" : "+r"(O[k]) : "r"(a[i]), "r"(a[j]));
+                else asm volatile("madc.lo.cc.u32 %0, %1, %2, %0;" : "+r"(O[k]) : "r"(a[i]), "r"(a[j]));
+                asm volatile("madc.hi.cc.u32 %0, %1, %2, %0;" : "+r"(O[k + 1]) : "r"(a[i]), "r"(a[j]));
+                last = k + 2;
+            }
+            asm volatile("addc.u32 %0, %0, 0;" : "+r"(O[last]));
+        }
+        if (i + 2 < 12) {   // i + j even -> A[i + j], A[i + j + 1]
+            int last = 0;
+#pragma unroll
+            for (int j = i + 2; j < 12; j += 2) {
+                const int k = i + j;
+                if (j == i + 2) asm volatile("mad.lo.cc.u32 %0, %1, %2, %0;" : "+r"(A[k]) : "r"(a[i]), "r"(a[j]));
+                else asm volatile("madc.lo.cc.u32 %0, %1, %2, %0;" : "+r"(A[k]) : "r"(a[i]), "r"(a[j]));
+                asm volatile("madc.hi.cc.u32 %0, %1, %2, %0;" : "+r"(A[k + 1]) : "r"(a[i]), "r"(a[j]));
+                last = k + 2;
+            }
+            asm volatile("addc.u32 %0, %0, 0;" : "+r"(A[last]));
+        }
+    }
+    // T = 2 * (A + (O << 32)) + sum_i a_i^2 2^(64 i);  columns 0 and 1 of the cross products are 0 and O[0]
+    uint32_t T[24];
+    T[1] = O[0];
+    asm volatile("add.cc.u32 %0, %1, %2;" : "=r"(T[2]) : "r"(A[2]), "r"(O[1]));
+#pragma unroll
+    for (int k = 3; k < 23; k++) asm volatile("addc.cc.u32 %0, %1, %2;" : "=r"(T[k]) : "r"(A[k]), "r"(O[k - 1]));
+    asm volatile("addc.u32 %0, %1, %2;" : "=r"(T[23]) : "r"(A[23]), "r"(O[22]));
+#pragma unroll
+    for (int k = 23; k >= 2; k--) T[k] = __funnelshift_l(T[k - 1], T[k], 1);
+    T[1] <<= 1;
+    T[0] = 0;
+    asm volatile("mad.lo.cc.u32 %0, %1, %1, %0;" : "+r"(T[0]) : "r"(a[0]));
+    asm volatile("madc.hi.cc.u32 %0, %1, %1, %0;" : "+r"(T[1]) : "r"(a[0]));
+#pragma unroll
+    for (int i = 1; i < 12; i++) {
+        asm volatile("madc.lo.cc.u32 %0, %1, %1, %0;" : "+r"(T[2 * i]) : "r"(a[i]));
+        if (i < 11) asm volatile("madc.hi.cc.u32 %0, %1, %1, %0;" : "+r"(T[2 * i + 1]) : "r"(a[i]));
+        else asm volatile("madc.hi.u32 %0, %1, %1, %0;" : "+r"(T[2 * i + 1]) : "r"(a[i]));
+    }
+    // Montgomery reduction of the low half: 12 rows, roles swapped as in fp_mul
+    uint32_t od[12];
+#pragma unroll
+    for (int k = 0; k < 12; k++) od[k] = 0;
+#pragma unroll
+    for (int i = 0; i < 12; i += 2) {
+        dg_redc_row(T, od);
+        dg_redc_row(od, T);
+    }
+    // live aligned array: T[0..11]; od is stale (od[k] belongs to column k - 1); then the high half.  (T + M p) / R < 1.2 p.
+    Fp r;
+    asm volatile("add.cc.u32 %0, %1, %2;" : "=r"(r.l[0]) : "r"(T[0]), "r"(od[1]));
+#pragma unroll
+    for (int i = 1; i < 11; i++) asm volatile("addc.cc.u32 %0, %1, %2;" : "=r"(r.l[i]) : "r"(T[i]), "r"(od[i + 1]));
+    asm volatile("addc.u32 %0, %1, 0;" : "=r"(r.l[11]) : "r"(T[11]));
+    asm volatile("add.cc.u32 %0, %0, %1;" : "+r"(r.l[0]) : "r"(T[12]));
+#pragma unroll
+    for (int i = 1; i < 11; i++) asm volatile("addc.cc.u32 %0, %0, %1;" : "+r"(r.l[i]) : "r"(T[12 + i]));
+    asm volatile("addc.u32 %0, %0, %1;" : "+r"(r.l[11]) : "r"(T[23]));
+    fp_final_sub(r);
+    return r;
+#endif
+}
 
 }  // namespace dg
 

@@ -22,6 +22,9 @@ static inline MsmGeom msm_geometry(size_t n, MsmPre pre, bool fp2 = false) {
             // terms up to at least 2^24 (2^15 buckets per window keep the reduction small, 8 x 16 = 128 bits exactly);
             // below that the window-combination chain dominates and about log2(n) - 3 bits are best
             c = logn >= 17 ? 16 : logn - 3;
+            // G2 (tools/sweep_g2.py): the bucket reduction costs 3x as much per bucket, so 10 windows of 13 bits beat 8 of 16
+            // up to 2^18 terms (7.40 vs 7.98 ms at 2^18); from 2^19 the accumulation dominates again (2^20: 19.0 vs 20.9 ms)
+            if (fp2 && (logn == 17 || logn == 18)) c = 13;
             if (c < 4) c = 4;
         } else {
             c = logn - 4;
@@ -286,11 +289,13 @@ static int32_t msm_run(const void *bases_dev, const void *scalars_dev, size_t n,
         XYZZ<F> *lines = red[0], *vbuf = red[1], *ws_out = red[2];
         constexpr unsigned QP = RedGeom<F>::QP;
         const size_t smem = sizeof(QuadWS<F>) * QP;
-        // G2: 12-lane quads for the line sums while every CTA is resident at once (the launch is latency-bound), 4-lane quads
-        // when the grid is several waves deep (tunable 6: 1 forces 4-lane, 2 forces 12-lane quads)
+        // G2: the line sums keep 4-lane quads.  Measured on B200 at 2^18 terms (tools/sweep_g2.py): 12-lane quads make this
+        // stage slower both when the grid is several waves deep (raw bases: 7.45 -> 7.62 ms) and when every CTA is resident
+        // at once (resident table: 7.63 -> 7.95 ms) -- the stage is bound by its ~2^16 additions, not by the chain length --
+        // while the short-grid stages after it (subset sums, window sums, window combination, hot-bucket sums) are 2x faster
+        // with them.  tunable 6 = 2 forces 12-lane quads here (A/B switch).
         constexpr bool W = QuadWide<F>::value;
-        const int force_w = ctx().tunable[6].load();
-        const bool wide_lines = W && (force_w == 2 || (force_w != 1 && (size_t)nlines * g.nwin <= (size_t)ctx().sm_count * 4));
+        const bool wide_lines = W && ctx().tunable[6].load() == 2;
         int32_t rc = smem_opt_in(k_red_lines<F, false>, smem);
         if (!rc && W) rc = smem_opt_in(k_red_lines<F, W>, smem);
         if (!rc) rc = smem_opt_in(k_red_subsets<F>, smem);

@@ -9,7 +9,7 @@ import os
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, 'libdockgpu.so')
+LIB_PATH = os.environ.get('DOCKGPU_LIB') or os.path.join(HERE, 'libdockgpu.so')      # DOCKGPU_LIB: A/B builds (tools/ab_bench.py)
 
 G1_AFF, G1_JAC, G2_AFF, G2_JAC, FP12, SCALAR = 96, 144, 192, 288, 576, 32
 

@@ -36,6 +36,25 @@ def test_fp_ops_vs_bigint(dg, op):
     assert out == exp
 
 
+def test_fp_sqr_dedicated(dg):
+    """The dedicated squaring (66 cross products + 12 squares + 12 reduction rows, fp.cuh) against Python integers, on raw
+    Montgomery representations chosen for their limb patterns (all-ones limbs, single bits, p - 1) and on random values;
+    the same inputs through the general multiplier must agree bit for bit."""
+    rng = np.random.default_rng(33)
+    rinv = pow(1 << 384, -1, o.P)
+    raws = [0, 1, 2, o.P - 1, o.P - 2, (1 << 380) - 1, (1 << 380), (1 << 380) + (1 << 379) - 1, (1 << 352) - 1, ((1 << 28) - 1) << 352,
+            0xffffffff, 0xffffffff00000000, (1 << 64) - 1, ((1 << 380) - 1) ^ ((1 << 190) - 1), int('55' * 47, 16), int('aa' * 47, 16) >> 3]
+    raws += [1 << k for k in range(0, 381, 5)] + [o.P - (1 << k) for k in range(0, 380, 9)]
+    raws += [((1 << 32) - 1) << (32 * k) for k in range(11)] + [(1 << 380) - 1 - (((1 << 32) - 1) << (32 * k)) for k in range(11)]
+    raws += [int.from_bytes(rng.bytes(48), 'little') % o.P for _ in range(4096)]
+    assert all(0 <= v < o.P for v in raws)
+    a = b''.join(v.to_bytes(48, 'little') for v in raws)
+    out = bytes(dg.dbg_fp_op(3, a, a))
+    exp = b''.join(o.fp_to_mont_bytes(pow(v * rinv % o.P, 2, o.P)) for v in raws)
+    assert out == exp
+    assert bytes(dg.dbg_fp_op(0, a, a)) == exp
+
+
 @pytest.mark.parametrize('op', [5, 6, 7])       # 5: Fermat, 6: bit-serial binary Euclid, 7: Pornin's binary GCD (31-bit inner rounds)
 def test_fp_inverse(dg, op):
     rng = np.random.default_rng(7)
