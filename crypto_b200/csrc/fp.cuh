@@ -224,6 +224,96 @@ __device__ __forceinline__ void dg_redc_row(uint32_t *al, uint32_t *of) {
     asm volatile("addc.u32 %0, %0, 0;" : "+r"(of[11]));                    // column 12
 }
 
+// T / 2^384 mod p for a 24-limb T < p * 2^384 (T is clobbered): the 12 reduction rows of the multiplier on the low half,
+// roles swapped as in fp_mul, then one addition of the high half.  (T + M p) / R < T / R + p < 2p: one final subtraction.
+__device__ __forceinline__ Fp fp_redc24(uint32_t *T) {
+    uint32_t od[12];
+#pragma unroll
+    for (int k = 0; k < 12; k++) od[k] = 0;
+#pragma unroll
+    for (int i = 0; i < 12; i += 2) {
+        dg_redc_row(T, od);
+        dg_redc_row(od, T);
+    }
+    // live aligned array: T[0..11]; od is stale (od[k] belongs to column k - 1)
+    Fp r;
+    asm volatile("add.cc.u32 %0, %1, %2;" : "=r"(r.l[0]) : "r"(T[0]), "r"(od[1]));
+#pragma unroll
+    for (int i = 1; i < 11; i++) asm volatile("addc.cc.u32 %0, %1, %2;" : "=r"(r.l[i]) : "r"(T[i]), "r"(od[i + 1]));
+    asm volatile("addc.u32 %0, %1, 0;" : "=r"(r.l[11]) : "r"(T[11]));
+    asm volatile("add.cc.u32 %0, %0, %1;" : "+r"(r.l[0]) : "r"(T[12]));
+#pragma unroll
+    for (int i = 1; i < 11; i++) asm volatile("addc.cc.u32 %0, %0, %1;" : "+r"(r.l[i]) : "r"(T[12 + i]));
+    asm volatile("addc.u32 %0, %0, %1;" : "+r"(r.l[11]) : "r"(T[23]));
+    fp_final_sub(r);
+    return r;
+}
+
+// six products {a[s], a[s + 2], ..} * b accumulated on acc[start .. start + 11] as one carry chain; the carry out lands in
+// acc[start + 12], a limb that holds nothing but earlier carries
+__device__ __forceinline__ void dg_wide_chain(uint32_t *acc, int start, const uint32_t *a, int s, uint32_t b) {
+    asm volatile("mad.lo.cc.u32 %0, %1, %2, %0;" : "+r"(acc[start]) : "r"(a[s]), "r"(b));
+    asm volatile("madc.hi.cc.u32 %0, %1, %2, %0;" : "+r"(acc[start + 1]) : "r"(a[s]), "r"(b));
+#pragma unroll
+    for (int t = 1; t < 6; t++) {
+        asm volatile("madc.lo.cc.u32 %0, %1, %2, %0;" : "+r"(acc[start + 2 * t]) : "r"(a[s + 2 * t]), "r"(b));
+        asm volatile("madc.hi.cc.u32 %0, %1, %2, %0;" : "+r"(acc[start + 2 * t + 1]) : "r"(a[s + 2 * t]), "r"(b));
+    }
+    if (start + 12 < 24) asm volatile("addc.u32 %0, %0, 0;" : "+r"(acc[start + 12]));
+}
+// T[0..23] = a * b as a plain integer (a, b < 2^384, a * b < 2^768): the 144 products of the multiplier without the
+// interleaved reduction rows, even/odd split over two 24-limb accumulators (A[k] = column k, O[k] = column k + 1)
+__device__ __forceinline__ void fp_mul_wide(uint32_t *T, const uint32_t *a, const uint32_t *b) {
+    uint32_t O[24];
+#pragma unroll
+    for (int j = 0; j < 12; j += 2) {
+        asm volatile("mul.lo.u32 %0, %1, %2;" : "=r"(T[j]) : "r"(a[j]), "r"(b[0]));
+        asm volatile("mul.hi.u32 %0, %1, %2;" : "=r"(T[j + 1]) : "r"(a[j]), "r"(b[0]));
+        asm volatile("mul.lo.u32 %0, %1, %2;" : "=r"(O[j]) : "r"(a[j + 1]), "r"(b[0]));
+        asm volatile("mul.hi.u32 %0, %1, %2;" : "=r"(O[j + 1]) : "r"(a[j + 1]), "r"(b[0]));
+    }
+#pragma unroll
+    for (int k = 12; k < 24; k++) { T[k] = 0; O[k] = 0; }
+#pragma unroll
+    for (int i = 1; i < 12; i++) {
+        if (i & 1) {
+            dg_wide_chain(O, i - 1, a, 0, b[i]);          // a_even * b_i: odd columns i + j -> O[i + j - 1]
+            dg_wide_chain(T, i + 1, a, 1, b[i]);          // a_odd * b_i: even columns i + j -> A[i + j]
+        } else {
+            dg_wide_chain(T, i, a, 0, b[i]);
+            dg_wide_chain(O, i, a, 1, b[i]);
+        }
+    }
+    asm volatile("add.cc.u32 %0, %0, %1;" : "+r"(T[1]) : "r"(O[0]));
+#pragma unroll
+    for (int k = 2; k < 23; k++) asm volatile("addc.cc.u32 %0, %0, %1;" : "+r"(T[k]) : "r"(O[k - 1]));
+    asm volatile("addc.u32 %0, %0, %1;" : "+r"(T[23]) : "r"(O[22]));
+}
+// 24-limb helpers for lazily reduced sums of products
+__device__ __forceinline__ void dg_sub24(uint32_t *a, const uint32_t *b) {                 // a -= b  (mod 2^768)
+    asm volatile("sub.cc.u32 %0, %0, %1;" : "+r"(a[0]) : "r"(b[0]));
+#pragma unroll
+    for (int k = 1; k < 23; k++) asm volatile("subc.cc.u32 %0, %0, %1;" : "+r"(a[k]) : "r"(b[k]));
+    asm volatile("subc.u32 %0, %0, %1;" : "+r"(a[23]) : "r"(b[23]));
+}
+__device__ __forceinline__ void dg_add24_psq(uint32_t *a) {                                 // a += p^2  (mod 2^768)
+    constexpr uint32_t Q[24] = {DG_PSQ0, DG_PSQ1, DG_PSQ2, DG_PSQ3, DG_PSQ4, DG_PSQ5, DG_PSQ6, DG_PSQ7, DG_PSQ8, DG_PSQ9, DG_PSQ10, DG_PSQ11,
+                                DG_PSQ12, DG_PSQ13, DG_PSQ14, DG_PSQ15, DG_PSQ16, DG_PSQ17, DG_PSQ18, DG_PSQ19, DG_PSQ20, DG_PSQ21, DG_PSQ22, DG_PSQ23};
+    asm volatile("add.cc.u32 %0, %0, %1;" : "+r"(a[0]) : "r"(Q[0]));
+#pragma unroll
+    for (int k = 1; k < 23; k++) asm volatile("addc.cc.u32 %0, %0, %1;" : "+r"(a[k]) : "r"(Q[k]));
+    asm volatile("addc.u32 %0, %0, %1;" : "+r"(a[23]) : "r"(Q[23]));
+}
+// a + b as a plain integer (no reduction; a, b < p gives < 2p < 2^382)
+__device__ __forceinline__ Fp fp_add_raw(const Fp &a, const Fp &b) {
+    Fp r;
+    asm volatile("add.cc.u32 %0, %1, %2;" : "=r"(r.l[0]) : "r"(a.l[0]), "r"(b.l[0]));
+#pragma unroll
+    for (int i = 1; i < 11; i++) asm volatile("addc.cc.u32 %0, %1, %2;" : "=r"(r.l[i]) : "r"(a.l[i]), "r"(b.l[i]));
+    asm volatile("addc.u32 %0, %1, %2;" : "=r"(r.l[11]) : "r"(a.l[11]), "r"(b.l[11]));
+    return r;
+}
+
 __device__ __forceinline__ Fp fp_sqr(const Fp &x) {
 #ifdef DG_FP_SQR_VIA_MUL
     return fp_mul(x, x);
@@ -289,27 +379,7 @@ __device__ __forceinline__ Fp fp_sqr(const Fp &x) {
         if (i < 11) asm volatile("madc.hi.cc.u32 %0, %1, %1, %0;" : "+r"(T[2 * i + 1]) : "r"(a[i]));
         else asm volatile("madc.hi.u32 %0, %1, %1, %0;" : "+r"(T[2 * i + 1]) : "r"(a[i]));
     }
-    // Montgomery reduction of the low half: 12 rows, roles swapped as in fp_mul
-    uint32_t od[12];
-#pragma unroll
-    for (int k = 0; k < 12; k++) od[k] = 0;
-#pragma unroll
-    for (int i = 0; i < 12; i += 2) {
-        dg_redc_row(T, od);
-        dg_redc_row(od, T);
-    }
-    // live aligned array: T[0..11]; od is stale (od[k] belongs to column k - 1); then the high half.  (T + M p) / R < 1.2 p.
-    Fp r;
-    asm volatile("add.cc.u32 %0, %1, %2;" : "=r"(r.l[0]) : "r"(T[0]), "r"(od[1]));
-#pragma unroll
-    for (int i = 1; i < 11; i++) asm volatile("addc.cc.u32 %0, %1, %2;" : "=r"(r.l[i]) : "r"(T[i]), "r"(od[i + 1]));
-    asm volatile("addc.u32 %0, %1, 0;" : "=r"(r.l[11]) : "r"(T[11]));
-    asm volatile("add.cc.u32 %0, %0, %1;" : "+r"(r.l[0]) : "r"(T[12]));
-#pragma unroll
-    for (int i = 1; i < 11; i++) asm volatile("addc.cc.u32 %0, %0, %1;" : "+r"(r.l[i]) : "r"(T[12 + i]));
-    asm volatile("addc.u32 %0, %0, %1;" : "+r"(r.l[11]) : "r"(T[23]));
-    fp_final_sub(r);
-    return r;
+    return fp_redc24(T);
 #endif
 }
 

@@ -29,6 +29,38 @@ template <> __device__ __forceinline__ Fp2 fone<Fp2>() { return {fp_one(), fp_ze
 // Every out-of-line function below follows the same rule: operands by value or copied into locals first.
 static __device__ __noinline__ Fp fp_mul_ni(Fp a, Fp b) { return fp_mul(a, b); }
 
+// Karatsuba with lazy reduction: the three 768-bit products a0 b0, a1 b1, (a0 + a1)(b0 + b1) are combined as plain
+// integers and only the two results are reduced -- 3 x 144 + 2 x 156 = 744 wide multiply-adds instead of 3 x 300 = 900.
+//   c1 = (a0 + a1)(b0 + b1) - a0 b0 - a1 b1 = a0 b1 + a1 b0  in [0, 2 p^2)
+//   c0 = a0 b0 - a1 b1 + p^2                                  in (0, 2 p^2)
+// both below p * 2^384 (2p < 2^384), so one Montgomery reduction each gives a value below 2p and fp_redc24's single final
+// subtraction makes it canonical.  Operands by value: see fp_mul_ni.
+#ifdef DG_FP2_MUL_LAZY
+static __device__ __noinline__ Fp2 fp2_mul_ni(Fp2 a, Fp2 b) {
+    uint32_t t0[24], t1[24], t2[24];
+    fp_mul_wide(t0, a.c0.l, b.c0.l);
+    fp_mul_wide(t1, a.c1.l, b.c1.l);
+    {
+        Fp sa = fp_add_raw(a.c0, a.c1), sb = fp_add_raw(b.c0, b.c1);
+        fp_mul_wide(t2, sa.l, sb.l);
+    }
+    dg_sub24(t2, t0);
+    dg_sub24(t2, t1);
+    dg_sub24(t0, t1);
+    dg_add24_psq(t0);
+    Fp2 r;
+    r.c0 = fp_redc24(t0);
+    r.c1 = fp_redc24(t2);
+    return r;
+}
+#endif
+// Measured on B200 (tools/ab_bench.py, G2 MSM at 2^18 terms): the lazy form is SLOWER than three out-of-line
+// multiplications -- 7.60 vs 7.41 ms on raw bases, 5.39 vs 5.30 ms through a table.  It saves 17 % of the multiply-adds
+// but needs 132 registers of its own (the batch-affine kernel around it already sits at the 254-register cap and spills
+// ~200 bytes more) and adds ~170 dependent 24-limb carry-chain additions.  Kept for the record behind DG_FP2_MUL_LAZY.
+#ifdef DG_FP2_MUL_LAZY
+__device__ __forceinline__ Fp2 fmul(const Fp2 &a, const Fp2 &b) { return fp2_mul_ni(a, b); }
+#else
 __device__ __forceinline__ Fp2 fmul(const Fp2 &a, const Fp2 &b) {
     Fp t0 = fp_mul_ni(a.c0, b.c0);
     Fp t1 = fp_mul_ni(a.c1, b.c1);
@@ -38,6 +70,7 @@ __device__ __forceinline__ Fp2 fmul(const Fp2 &a, const Fp2 &b) {
     r.c1 = fp_sub(fp_sub(m, t0), t1);
     return r;
 }
+#endif
 __device__ __forceinline__ Fp2 fsqr(const Fp2 &a) {
     Fp s = fp_add(a.c0, a.c1), d = fp_sub(a.c0, a.c1);
     Fp m = fp_mul_ni(a.c0, a.c1);

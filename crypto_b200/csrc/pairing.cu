@@ -82,14 +82,7 @@ __device__ __forceinline__ Fp fp_half(const Fp &a) {
 // values are added as plain integers (one 12-limb carry chain each, no trial subtraction) and brought back below p by
 // three conditional subtractions of 4p, 2p, p -- about half the instructions of six modular additions, all of them on
 // the stage's critical path.
-__device__ __forceinline__ Fp fp_add_raw(const Fp &a, const Fp &b) {
-    Fp r;
-    asm volatile("add.cc.u32 %0, %1, %2;" : "=r"(r.l[0]) : "r"(a.l[0]), "r"(b.l[0]));
-#pragma unroll
-    for (int i = 1; i < 11; i++) asm volatile("addc.cc.u32 %0, %1, %2;" : "=r"(r.l[i]) : "r"(a.l[i]), "r"(b.l[i]));
-    asm volatile("addc.u32 %0, %1, %2;" : "=r"(r.l[11]) : "r"(a.l[11]), "r"(b.l[11]));
-    return r;
-}
+// (fp_add_raw: fp.cuh)
 template <int K> __device__ __forceinline__ void fp_csub_kp(Fp &a) {          // a -= K p when a >= K p  (K = 1, 2, 4)
     uint32_t t[12], br;
     constexpr int SH = K == 4 ? 2 : K == 2 ? 1 : 0;
