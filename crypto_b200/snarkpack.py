@@ -9,6 +9,9 @@ Same structure, names and relations as legogroth16/src/aggregation/:
   * kzg.rs:32-343           KZG openings of the final commitment keys (product-form polynomials of the GIPA challenges)
   * groth16/prover.rs:46-382    aggregate_proofs, prove_tipp_mipp, gipa_tipp_mipp
   * groth16/verifier.rs:34-454  verify_aggregate_proof, verify_tipp_mipp, gipa_verify_tipp_mipp
+  * legogroth16/prover.rs:47-424, verifier.rs:48-330   aggregate_lego_proofs / verify_aggregate_lego_proof: the same
+                            protocol with a second MIPP for the D commitments (com_d, z_d, comms_d, final_d)
+  * legogroth16/using_groth16.rs:27-128   LegoGroth16 proofs through the Groth16 aggregate with the D's in the clear
 The Fiat-Shamir transcript is a hash chain (the reference's Merlin transcript is outside the hot path); everything that
 costs curve arithmetic runs on the GPU: per GIPA round TEN pairing products go out as ONE dg_multi_pairing_batch call,
 the vector foldings are dg_compress_g1/g2, key scaling is dg_batch_mul, the MIPP inner products and the KZG quotient
@@ -18,7 +21,7 @@ Group elements are packed Montgomery records (bytes); vectors are lists of recor
 """
 import hashlib
 from dataclasses import dataclass
-from typing import List, Tuple
+from typing import List, Optional, Tuple
 
 import numpy as np
 
@@ -252,10 +255,16 @@ class GipaProof:
     final_c: bytes
     final_vkey: Tuple[bytes, bytes]
     final_wkey: Tuple[bytes, bytes]
+    # LegoGroth16 aggregation (GipaProofLego, aggregation/legogroth16/proof.rs:79-95): the same MIPP once more for the D's
+    comms_d: Optional[list] = None
+    z_d: Optional[list] = None
+    final_d: Optional[bytes] = None
 
 
 @dataclass
 class AggregateProof:
+    """AggregateProof (aggregation/groth16/proof.rs) or, with com_d / z_d set, AggregateLegoProof
+    (aggregation/legogroth16/proof.rs:22-42)."""
     com_ab: Tuple[bytes, bytes]
     com_c: Tuple[bytes, bytes]
     z_ab: bytes
@@ -263,13 +272,27 @@ class AggregateProof:
     gipa: GipaProof
     vkey_opening: Tuple[bytes, bytes]
     wkey_opening: Tuple[bytes, bytes]
+    com_d: Optional[Tuple[bytes, bytes]] = None
+    z_d: Optional[bytes] = None
+
+    @property
+    def is_lego(self):
+        return self.com_d is not None
 
 
-def gipa_tipp_mipp(transcript, a, b, c, vkey: Key, wkey: Key, r, ip_ab, agg_c):
+def gipa_tipp_mipp(transcript, a, b, c, vkey: Key, wkey: Key, r, ip_ab, agg_c, d=None, agg_d=None):
+    """GIPA recursion for TIPP (A, B) and MIPP (C, r) -- aggregation/groth16/prover.rs:196-357 -- and, when d is given, the
+    second MIPP (D, r) of the LegoGroth16 variant (aggregation/legogroth16/prover.rs:216-424): per round the ten (fourteen)
+    pairing products go to the GPU in one call, the z values are two (four) MSMs."""
+    lego = d is not None
     m_a, m_b, m_c, m_r = list(a), list(b), list(c), list(r)
+    m_d = list(d) if lego else None
     comms_ab, comms_c, z_ab, z_c, challenges, challenges_inv = [], [], [], [], [], []
+    comms_d, z_d = [], []
     transcript.append(b'inner-product-ab', ip_ab)
     transcript.append(b'comm-c', agg_c)
+    if lego:
+        transcript.append(b'comm-d', agg_d)
     c_inv = transcript.challenge_scalar(b'first-challenge')
     ch = _inv(c_inv)
     i = 0
@@ -283,20 +306,35 @@ def gipa_tipp_mipp(transcript, a, b, c, vkey: Key, wkey: Key, r, ip_ab, agg_c):
         # MIPP: tuc_l = single(vk_l, c_r), tuc_r = single(vk_r, c_l): ten pairing products, one device call
         prods = (commit_double_products(vk_l, wk_r, a_r, b_l) + commit_double_products(vk_r, wk_l, a_l, b_r) +
                  [(a_r, b_l), (a_l, b_r)] + commit_single_products(vk_l, c_r) + commit_single_products(vk_r, c_l))
+        if lego:
+            d_l, d_r = m_d[:split], m_d[split:]
+            prods += commit_single_products(vk_l, d_r) + commit_single_products(vk_r, d_l)
         gt = _pairing_products(prods)
         tab_l, tab_r, zab_l, zab_r, tuc_l, tuc_r = (gt[0], gt[1]), (gt[2], gt[3]), gt[4], gt[5], (gt[6], gt[7]), (gt[8], gt[9])
         zc_l = gp.into_affine(bytes(lib.msm(_cat(c_r), gp.fr_to_bytes(r_l))))      # c[n':] ^ r[:n']
         zc_r = gp.into_affine(bytes(lib.msm(_cat(c_l), gp.fr_to_bytes(r_r))))      # c[:n'] ^ r[n':]
+        if lego:
+            tud_l, tud_r = (gt[10], gt[11]), (gt[12], gt[13])
+            zd_l = gp.into_affine(bytes(lib.msm(_cat(d_r), gp.fr_to_bytes(r_l))))
+            zd_r = gp.into_affine(bytes(lib.msm(_cat(d_l), gp.fr_to_bytes(r_r))))
         if i > 0:
             transcript.append(b'c_inv', c_inv)
-            for label, val in ((b'zab_l', zab_l), (b'zab_r', zab_r), (b'zc_l', zc_l), (b'zc_r', zc_r), (b'tab_l', tab_l), (b'tab_r', tab_r),
-                               (b'tuc_l', tuc_l), (b'tuc_r', tuc_r)):
+            labelled = [(b'zab_l', zab_l), (b'zab_r', zab_r), (b'zc_l', zc_l), (b'zc_r', zc_r)]
+            if lego:
+                labelled += [(b'zd_l', zd_l), (b'zd_r', zd_r)]
+            labelled += [(b'tab_l', tab_l), (b'tab_r', tab_r), (b'tuc_l', tuc_l), (b'tuc_r', tuc_r)]
+            if lego:
+                labelled += [(b'tud_l', tud_l), (b'tud_r', tud_r)]
+            for label, val in labelled:
                 transcript.append(label, val)
             c_inv = transcript.challenge_scalar(b'challenge_i')
             ch = _inv(c_inv)
         m_a = compress(m_a, split, ch)
         m_b = compress(m_b, split, c_inv, G2)
         m_c = compress(m_c, split, ch)
+        if lego:
+            m_d = compress(m_d, split, ch)
+            comms_d.append((tud_l, tud_r)); z_d.append((zd_l, zd_r))
         m_r = [(x + y * c_inv) % R_MODULUS for x, y in zip(r_l, r_r)]
         vkey = vk_l.compress(vk_r, c_inv)
         wkey = wk_l.compress(wk_r, ch)
@@ -305,11 +343,30 @@ def gipa_tipp_mipp(transcript, a, b, c, vkey: Key, wkey: Key, r, ip_ab, agg_c):
         challenges.append(ch); challenges_inv.append(c_inv)
         i += 1
     proof = GipaProof(len(a), comms_ab, comms_c, z_ab, z_c, m_a[0], m_b[0], m_c[0], vkey.first(), wkey.first())
+    if lego:
+        proof.comms_d, proof.z_d, proof.final_d = comms_d, z_d, m_d[0]
     return proof, challenges, challenges_inv
 
 
 def aggregate_proofs(srs: ProverSRS, transcript: Transcript, proofs):
-    """proofs: list of (A, B, C) Groth16 proofs (affine records); the count must be a power of two >= 2."""
+    """proofs: list of (A, B, C) Groth16 proofs (affine records); the count must be a power of two >= 2
+    (aggregation/groth16/prover.rs:46-148)."""
+    return _aggregate(srs, transcript, proofs, False)
+
+
+def aggregate_lego_proofs(srs: ProverSRS, transcript: Transcript, proofs):
+    """proofs: list of (A, B, C, D) LegoGroth16 proofs; the D's get their own pair commitment, z_d = sum r^i D_i and MIPP
+    (aggregation/legogroth16/prover.rs:47-156)."""
+    return _aggregate(srs, transcript, proofs, True)
+
+
+def aggregate_lego_proofs_using_groth16(srs: ProverSRS, transcript: Transcript, proofs):
+    """LegoGroth16 proofs aggregated with the Groth16 protocol, the D's handed to the verifier in the clear
+    (aggregation/legogroth16/using_groth16.rs:27-45) -> (AggregateProof, [D_i])."""
+    return _aggregate(srs, transcript, [p[:3] for p in proofs], False), [p[3] for p in proofs]
+
+
+def _aggregate(srs: ProverSRS, transcript: Transcript, proofs, lego):
     n = len(proofs)
     if n < 2:
         raise ValueError('InvalidProof: invalid proof size < 2')
@@ -318,18 +375,24 @@ def aggregate_proofs(srs: ProverSRS, transcript: Transcript, proofs):
     if not srs.has_correct_len(n):
         raise ValueError('InvalidSRS: SRS len %d != proofs len %d' % (len(srs.vkey), n))
     a, b, c = [p[0] for p in proofs], [p[1] for p in proofs], [p[2] for p in proofs]
-    gt = _pairing_products(commit_double_products(srs.vkey, srs.wkey, a, b) + commit_single_products(srs.vkey, c))
+    d = [p[3] for p in proofs] if lego else None
+    gt = _pairing_products(commit_double_products(srs.vkey, srs.wkey, a, b) + commit_single_products(srs.vkey, c) +
+                           (commit_single_products(srs.vkey, d) if lego else []))
     com_ab, com_c = (gt[0], gt[1]), (gt[2], gt[3])
+    com_d = (gt[4], gt[5]) if lego else None
     transcript.append(b'AB-commitment', com_ab)
     transcript.append(b'C-commitment', com_c)
+    if lego:
+        transcript.append(b'D-commitment', com_d)
     r = transcript.challenge_scalar(b'r-random-fiatshamir')
     r_vec = powers(r, n)
     r_inv = [_inv(x) for x in r_vec]
     b_r = _split_records(lib.normalize_batch(lib.batch_mul(_cat(b), gp.fr_to_bytes(r_vec), g2=True), g2=True), 192)   # B^r
     z_ab = _pairing_products([(a, b_r)])[0]
     z_c = gp.into_affine(bytes(lib.msm(_cat(c), gp.fr_to_bytes(r_vec))))
+    z_d = gp.into_affine(bytes(lib.msm(_cat(d), gp.fr_to_bytes(r_vec)))) if lego else None
     wkey_r_inv = srs.wkey.scale(r_inv)
-    gipa, challenges, challenges_inv = gipa_tipp_mipp(transcript, a, b_r, c, srs.vkey, wkey_r_inv, r_vec, z_ab, z_c)
+    gipa, challenges, challenges_inv = gipa_tipp_mipp(transcript, a, b_r, c, srs.vkey, wkey_r_inv, r_vec, z_ab, z_c, d, z_d)
     challenges.reverse()
     challenges_inv.reverse()
     r_inverse = _inv(r_vec[1])
@@ -339,22 +402,30 @@ def aggregate_proofs(srs: ProverSRS, transcript: Transcript, proofs):
     z = transcript.challenge_scalar(b'z-challenge')
     vkey_opening = prove_commitment_v(srs.h_alpha_powers_table, srs.h_beta_powers_table, challenges_inv, z)
     wkey_opening = prove_commitment_w(srs.g_alpha_powers_table, srs.g_beta_powers_table, challenges, r_inverse, z)
-    return AggregateProof(com_ab, com_c, z_ab, z_c, gipa, vkey_opening, wkey_opening)
+    return AggregateProof(com_ab, com_c, z_ab, z_c, gipa, vkey_opening, wkey_opening, com_d, z_d)
 
 
 # ---- verifier ---------------------------------------------------------------------------------------------------------------
 def gipa_verify_tipp_mipp(proof: AggregateProof, r_shift, transcript):
     gipa = proof.gipa
+    lego = proof.is_lego
     challenges, challenges_inv = [], []
     transcript.append(b'inner-product-ab', proof.z_ab)
     transcript.append(b'comm-c', proof.z_c)
+    if lego:
+        transcript.append(b'comm-d', proof.z_d)
     c_inv = transcript.challenge_scalar(b'first-challenge')
     ch = _inv(c_inv)
     for i, ((tab_l, tab_r), (zab_l, zab_r), (tuc_l, tuc_r), (zc_l, zc_r)) in enumerate(zip(gipa.comms_ab, gipa.z_ab, gipa.comms_c, gipa.z_c)):
         if i > 0:
             transcript.append(b'c_inv', c_inv)
-            for label, val in ((b'zab_l', zab_l), (b'zab_r', zab_r), (b'zc_l', zc_l), (b'zc_r', zc_r), (b'tab_l', tab_l), (b'tab_r', tab_r),
-                               (b'tuc_l', tuc_l), (b'tuc_r', tuc_r)):
+            labelled = [(b'zab_l', zab_l), (b'zab_r', zab_r), (b'zc_l', zc_l), (b'zc_r', zc_r)]
+            if lego:
+                labelled += [(b'zd_l', gipa.z_d[i][0]), (b'zd_r', gipa.z_d[i][1])]
+            labelled += [(b'tab_l', tab_l), (b'tab_r', tab_r), (b'tuc_l', tuc_l), (b'tuc_r', tuc_r)]
+            if lego:
+                labelled += [(b'tud_l', gipa.comms_d[i][0]), (b'tud_r', gipa.comms_d[i][1])]
+            for label, val in labelled:
                 transcript.append(label, val)
             c_inv = transcript.challenge_scalar(b'challenge_i')
             ch = _inv(c_inv)
@@ -370,6 +441,13 @@ def gipa_verify_tipp_mipp(proof: AggregateProof, r_shift, transcript):
                                  ('tc', tuc_l[0], tuc_r[0]), ('uc', tuc_l[1], tuc_r[1])):
             res[key] = pc.gt_add(res[key], pc.gt_add(pc.gt_mul_bigint(left, c_), pc.gt_mul_bigint(right, ci_)))
     res['zc'] = gp.into_affine(zc)
+    if lego:
+        res['td'], res['ud'] = proof.com_d
+        zd_b = [p for pair in gipa.z_d for p in pair]
+        res['zd'] = gp.into_affine(gp.add([gp.to_projective(proof.z_d), bytes(lib.msm(_cat(zd_b), gp.fr_to_bytes(z_s)))]))
+        for (tud_l, tud_r), c_, ci_ in zip(gipa.comms_d, challenges, challenges_inv):
+            for key, left, right in (('td', tud_l[0], tud_r[0]), ('ud', tud_l[1], tud_r[1])):
+                res[key] = pc.gt_add(res[key], pc.gt_add(pc.gt_mul_bigint(left, c_), pc.gt_mul_bigint(right, ci_)))
     challenges.reverse()
     challenges_inv.reverse()
     final_r = polynomial_evaluation_product_form_from_transcript(challenges_inv, r_shift, 1)
@@ -405,7 +483,12 @@ def verify_tipp_mipp(v: VerifierSRS, proof: AggregateProof, r_shift, transcript,
     checker.add_multiple_sources_and_target([g.final_a, g.final_wkey[1]], [g.final_vkey[1], g.final_b], final_res['uab'])
     checker.add_multiple_sources_and_target([g.final_c], [g.final_vkey[0]], final_res['tc'])
     checker.add_multiple_sources_and_target([g.final_c], [g.final_vkey[1]], final_res['uc'])
-    return gp.mul_affine(g.final_c, final_r) == final_res['zc']
+    ok = gp.mul_affine(g.final_c, final_r) == final_res['zc']
+    if proof.is_lego:                                           # MIPP for D (aggregation/legogroth16/verifier.rs:194-223)
+        checker.add_multiple_sources_and_target([g.final_d], [g.final_vkey[0]], final_res['td'])
+        checker.add_multiple_sources_and_target([g.final_d], [g.final_vkey[1]], final_res['ud'])
+        ok = ok and gp.mul_affine(g.final_d, final_r) == final_res['zd']
+    return ok
 
 
 def aggregate_public_inputs(public_inputs, r_powers, r_sum, gamma_abc_g1: bytes):
@@ -415,18 +498,41 @@ def aggregate_public_inputs(public_inputs, r_powers, r_sum, gamma_abc_g1: bytes)
     return gp.into_affine(bytes(lib.msm(np.frombuffer(gamma_abc_g1, dtype=np.uint8), gp.fr_to_bytes(scalars))))
 
 
-def verify_aggregate_proof(v: VerifierSRS, vk, public_inputs, proof: AggregateProof, transcript: Transcript, checker_random, lazy=True):
+def verify_aggregate_lego_proof(v: VerifierSRS, vk, public_inputs, proof: AggregateProof, transcript: Transcript, checker_random, lazy=True):
+    """aggregation/legogroth16/verifier.rs:48-112: the D commitment joins the transcript, the D MIPP joins the checker and
+    z_d pairs with gamma in the final product."""
+    if not proof.is_lego or proof.gipa.comms_d is None or proof.gipa.z_d is None or proof.gipa.final_d is None:
+        return False
+    return verify_aggregate_proof(v, vk, public_inputs, proof, transcript, checker_random, lazy)
+
+
+def verify_aggregate_lego_proof_using_groth16(v: VerifierSRS, vk, public_inputs, proof: AggregateProof, d, transcript: Transcript,
+                                              checker_random, lazy=True):
+    """aggregation/legogroth16/using_groth16.rs:47-128: a Groth16 aggregate plus the D's in the clear; the verifier folds
+    sum r^i D_i into the public-input term itself."""
+    if proof.is_lego or len(d) != proof.gipa.nproofs:
+        return False
+    return verify_aggregate_proof(v, vk, public_inputs, proof, transcript, checker_random, lazy, clear_d=d)
+
+
+def verify_aggregate_proof(v: VerifierSRS, vk, public_inputs, proof: AggregateProof, transcript: Transcript, checker_random, lazy=True,
+                           clear_d=None):
     """vk: crypto_b200.groth16.VerifyingKey of the aggregated circuit; public_inputs: one list per proof."""
     n = proof.gipa.nproofs
     rounds = n.bit_length() - 1
-    if n < 2 or n & (n - 1) or any(len(x) != rounds for x in (proof.gipa.comms_ab, proof.gipa.comms_c, proof.gipa.z_ab, proof.gipa.z_c)):
+    vectors = [proof.gipa.comms_ab, proof.gipa.comms_c, proof.gipa.z_ab, proof.gipa.z_c]
+    if proof.is_lego:
+        vectors += [proof.gipa.comms_d, proof.gipa.z_d]
+    if n < 2 or n & (n - 1) or any(x is None or len(x) != rounds for x in vectors):
         return False                                            # parsing_check
-    if any(len(p) + 1 != len(vk.gamma_abc_g1) // 96 for p in public_inputs):
+    if any(len(p) + 1 > len(vk.gamma_abc_g1) // 96 for p in public_inputs):      # (the MSM truncates to the shorter side)
         raise ValueError('MalformedVerifyingKey')
     if len(public_inputs) != n:
         return False
     transcript.append(b'AB-commitment', proof.com_ab)
     transcript.append(b'C-commitment', proof.com_c)
+    if proof.is_lego:
+        transcript.append(b'D-commitment', proof.com_d)
     r = transcript.challenge_scalar(b'r-random-fiatshamir')
     checker = pc.RandomizedPairingChecker.new(checker_random, lazy)
     if not verify_tipp_mipp(v, proof, r, transcript, checker):
@@ -434,7 +540,14 @@ def verify_aggregate_proof(v: VerifierSRS, vk, public_inputs, proof: AggregatePr
     # final_verification_check: prod e(A_i, B_i)^(r^i) == e(alpha^(sum r^i), beta) e(agg inputs, gamma) e(z_c, delta)
     r_powers = powers(r, n)
     r_sum = sum(r_powers) % R_MODULUS
-    source1 = [gp.mul_affine(vk.alpha_g1, r_sum), aggregate_public_inputs(public_inputs, r_powers, r_sum, vk.gamma_abc_g1), proof.z_c]
+    inp = aggregate_public_inputs(public_inputs, r_powers, r_sum, vk.gamma_abc_g1)
+    if clear_d is not None:                                     # using_groth16.rs:106-114: (sum r^i D_i + inputs) pairs with gamma
+        d_r = bytes(lib.msm(_cat(clear_d), gp.fr_to_bytes(r_powers)))
+        inp = gp.into_affine(gp.add([d_r, gp.to_projective(inp)]))
+    source1 = [gp.mul_affine(vk.alpha_g1, r_sum), inp, proof.z_c]
     source2 = [vk.beta_g2, vk.gamma_g2, vk.delta_g2]
+    if proof.is_lego:                                           # legogroth16/verifier.rs:92-96
+        source1.insert(0, proof.z_d)
+        source2.insert(0, vk.gamma_g2)
     checker.add_multiple_sources_and_target(source1, source2, proof.z_ab)
     return checker.verify()
