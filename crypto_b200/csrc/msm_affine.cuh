@@ -39,6 +39,9 @@ namespace dg {
 
 #define DG_BA_THREADS 128
 #define DG_BA_WARPS (DG_BA_THREADS / 32)
+#ifndef DG_BA_G2_CTAS
+#define DG_BA_G2_CTAS 2          // resident CTAs per SM of the G2 instance (254 registers); 3 (168 registers) spills: measured slower
+#endif
 
 // out-of-line multiplier for the once-per-batch phase 2 (keeps the kernel inside the instruction cache)
 static __device__ __noinline__ Fp ba_mul(Fp a, Fp b) { return fp_mul(a, b); }
@@ -126,7 +129,7 @@ template <class F> __device__ __forceinline__ F ba_pre_load(const uint4 *pre, ui
 // 4 CTAs / SM at 128 registers (G1).  Measured: capping the allocation at 96 registers for 5 CTAs / SM spills ~200 bytes
 // per thread and is 4 % slower end to end (7.34 vs 7.04 ms at 2^20 terms).
 template <class F, bool GATHER>
-__global__ void __launch_bounds__(DG_BA_THREADS, (sizeof(F) > 48 ? 2 : 4))
+__global__ void __launch_bounds__(DG_BA_THREADS, (sizeof(F) > 48 ? DG_BA_G2_CTAS : 4))
     k_affine_round(const Affine<F> *__restrict__ in, const uint32_t *__restrict__ entries, const uint32_t *__restrict__ off_in,
                    const uint32_t *__restrict__ off_out, uint32_t nb, uint32_t K, Affine<F> *__restrict__ out,
                    uint4 *__restrict__ pre) {

@@ -86,7 +86,7 @@ template <class F> static inline MsmLayout msm_layout(size_t n, MsmPre pre) {
     int min_waves = ctx().tunable[0].load();
     if (min_waves < 1) min_waves = 1;
     size_t kmax = ctx().tunable[3].load() > 0 ? (size_t)ctx().tunable[3].load() : 128;
-    const size_t ba_threads = (size_t)ctx().sm_count * (sizeof(F) > 48 ? 2 : 4) * DG_BA_THREADS;     // one resident wave
+    const size_t ba_threads = (size_t)ctx().sm_count * (sizeof(F) > 48 ? DG_BA_G2_CTAS : 4) * DG_BA_THREADS;     // one resident wave
     for (int r = 0; r < m.R; r++) {
         size_t waves = (m.mb[r + 1] + ba_threads * kmax - 1) / (ba_threads * kmax);
         if (waves < (size_t)min_waves) waves = min_waves;
