@@ -332,7 +332,7 @@ __global__ void __launch_bounds__(128) k_bucket_fixup(const uint32_t *__restrict
 // the 27 operations per level x 5..6 levels of a multi-level running-sum scheme (measured 0.69 ms at
 // N = 2^15, all of it latency; this scheme 0.24 ms).
 template <class F> struct RedGeom {
-    static constexpr int QP = sizeof(F) > 48 ? 16 : 32;                     // quads per CTA (48 KB of workspace)
+    static constexpr int QP = sizeof(F) > 48 ? 16 : 32;                     // quads per CTA (33 KB of workspace)
     static constexpr int threads(bool wide) { return wide ? QuadLanes<true>::cta_threads(QP) : QuadLanes<false>::cta_threads(QP); }
     static constexpr int THREADS = threads(QuadWide<F>::value);             // 128 (G1: 4 lanes per quad), 256 (G2: 12 lanes per quad)
 };
@@ -344,7 +344,7 @@ __device__ __forceinline__ void red_cta_sum_fn(QuadWS<F> *wsall, uint32_t count,
     constexpr int QP = RedGeom<F>::QP;
     const uint32_t qi = qc.qi;
     QuadWS<F> &ws = wsall[qi];
-    enum { ACC = 1, ITEM = 2 };
+    enum { ACC = DG_Q_ACC, ITEM = DG_Q_ITEM };
     if (qc.active) {
         quad_set_inf(ws, ACC, qc);
         for (uint32_t k = qi; k < count; k += QP) {
@@ -399,7 +399,7 @@ __global__ void __launch_bounds__(RedGeom<F>::THREADS) k_fixup_long_part(const u
             const uint32_t j = lo + k;
             return (j == 0 && !first0) ? &tail[t0] : &head[t0 + j];
         }, qc);
-        if (qc.active && qc.qi == 0) quad_store(wsall[0], 1, &part[(size_t)i * DG_LONG_SPLIT + si], qc);
+        if (qc.active && qc.qi == 0) quad_store(wsall[0], DG_Q_ACC, &part[(size_t)i * DG_LONG_SPLIT + si], qc);
         __syncthreads();                                                                  // workspace is reused by the next item
     }
 }
@@ -416,7 +416,7 @@ __global__ void __launch_bounds__(RedGeom<F>::THREADS) k_fixup_long_final(const 
         const uint32_t s = off[b], e = off[b + 1];
         const uint32_t np = (e - 1) / L - s / L + 1;
         red_cta_sum<F>(wsall, part + (size_t)i * DG_LONG_SPLIT, long_split<F>(np), 1, -1, qc);
-        if (qc.active && qc.qi == 0) quad_store(wsall[0], 1, &buckets[b], qc);
+        if (qc.active && qc.qi == 0) quad_store(wsall[0], DG_Q_ACC, &buckets[b], qc);
         __syncthreads();
     }
 }
@@ -432,7 +432,7 @@ __global__ void __launch_bounds__(RedGeom<F>::threads(WIDE)) k_red_lines(const X
     const XYZZ<F> *bw = buckets + (size_t)w * nbw;
     if (line < nrows) red_cta_sum<F>(wsall, bw + (size_t)line * ncols, ncols, 1, -1, qc);            // row h: contiguous
     else red_cta_sum<F>(wsall, bw + (line - nrows), nrows, ncols, -1, qc);                            // column l: stride 2^LO
-    if (qc.active && qc.qi == 0) quad_store(wsall[0], 1, &lines[(size_t)w * line_stride + line], qc);
+    if (qc.active && qc.qi == 0) quad_store(wsall[0], DG_Q_ACC, &lines[(size_t)w * line_stride + line], qc);
 }
 
 // stage B: V_j = 2^j U_j for j < LO + HI, V_{LO+HI} = T.  grid (LO + HI + 1, nwin)
@@ -452,8 +452,8 @@ __global__ void __launch_bounds__(RedGeom<F>::THREADS) k_red_subsets(const XYZZ<
         QuadWS<F> &ws = wsall[0];
         if (j < LO + HI)
             for (int k = 0; k < j; k++)
-                if (!fis_zero(ws.v[4 * 1 + 2])) quad_dbl(ws, 1, 1, qc);
-        quad_store(ws, 1, &vout[(size_t)w * v_stride + j], qc);
+                if (!fis_zero(ws.v[4 * DG_Q_ACC + 2])) quad_dbl(ws, DG_Q_ACC, DG_Q_ACC, qc);
+        quad_store(ws, DG_Q_ACC, &vout[(size_t)w * v_stride + j], qc);
     }
 }
 
@@ -466,7 +466,7 @@ __global__ void __launch_bounds__(RedGeom<F>::THREADS) k_red_final(const XYZZ<F>
     QuadCtx qc = quad_ctx<QuadWide<F>::value>();
     const uint32_t w = blockIdx.y;
     red_cta_sum<F>(wsall, v + (size_t)w * v_stride, (uint32_t)nv, 1, -1, qc);
-    if (qc.active && qc.qi == 0) quad_store(wsall[0], 1, &wsum[(size_t)w * wsum_stride], qc);
+    if (qc.active && qc.qi == 0) quad_store(wsall[0], DG_Q_ACC, &wsum[(size_t)w * wsum_stride], qc);
 }
 
 // window sums S_w (one XYZZ per window at stride) -> sum_w 2^(c w) S_w, Horner from the top,
@@ -477,7 +477,7 @@ __global__ void __launch_bounds__(32) k_window_combine(const XYZZ<F> *__restrict
     QuadWS<F> &ws = reinterpret_cast<QuadWS<F> *>(dg_smem_quad)[0];
     QuadCtx qc = quad_ctx<QuadWide<F>::value>();
     if (!qc.active || qc.qi != 0 || blockIdx.x != 0) return;
-    enum { ACC = 1, ITEM = 2 };
+    enum { ACC = DG_Q_ACC, ITEM = DG_Q_ITEM };
     quad_load(ws, ACC, &wsum[(size_t)(nwin - 1) * stride], qc);
     for (int w = nwin - 2; w >= 0; w--) {
         for (int k = 0; k < c; k++)

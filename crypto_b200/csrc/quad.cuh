@@ -19,10 +19,14 @@
 
 namespace dg {
 
-// workspace slots: object k (an XYZZ point) lives in v[4k .. 4k+3] = X, Y, ZZ, ZZZ
-#define DG_Q_OBJS 4          // run, acc, item, spare
+// workspace slots: object k (an XYZZ point) lives in v[4k .. 4k+3] = X, Y, ZZ, ZZZ; the 14 temporaries of an addition follow.
+// Two objects (accumulator, item) + temporaries = 22 field elements per quad: 33 KB per CTA of 32 (G1) / 16 (G2) quads, so
+// the register file (5 CTAs/SM at 96 registers), not shared memory, bounds the residency of the line-sum kernel.
+#define DG_Q_OBJS 2          // acc, item
+#define DG_Q_ACC 0
+#define DG_Q_ITEM 1
 #define DG_Q_TMP (4 * DG_Q_OBJS)
-template <class F> struct QuadWS { F v[DG_Q_TMP + 16]; };
+template <class F> struct QuadWS { F v[DG_Q_TMP + 14]; };
 
 struct QuadCtx {
     uint32_t ql;        // member within the quad, 0..3
