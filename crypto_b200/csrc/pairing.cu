@@ -31,7 +31,11 @@ namespace dg {
 // The engine's small linear stages give different workers different jobs ("worker 0: e = ..., worker 1: h = ...");
 // as lanes of ONE warp those jobs would run one after the other (divergence), as lanes of different warps they run
 // side by side on the four schedulers.  Every function below indexes its work by this id only.
-__device__ __forceinline__ int pair_wid() { return (int)((threadIdx.x & 31u) * 4u + (threadIdx.x >> 5)); }
+__device__ __forceinline__ int pair_wid() { return (int)((threadIdx.x & 31u) * 4u + ((threadIdx.x >> 5) & 3u)); }
+// An engine is a GROUP of 128 threads (4 warps); a CTA holds one group (most kernels) or two (k_miller: one group walks
+// the G2 point and produces the lines, the other consumes them into f).  Every engine function synchronises its own
+// group only, on named barrier 1 + group.
+__device__ __forceinline__ void pair_sync() { asm volatile("bar.sync %0, 128;" ::"r"(1u + (threadIdx.x >> 7)) : "memory"); }
 
 // Fp12 in shared/global memory: 12 Fp in ark order (c0.c0.c0, c0.c0.c1, c0.c1.c0, ..., c1.c2.c1).
 // Flattened basis: coefficient of w^k (an Fp2) lives at tower position (i = k&1, j = k>>1).
@@ -45,11 +49,16 @@ static __device__ __forceinline__ Fp fp_mul_smem(const Fp *a, const Fp *b) { ret
 // One Karatsuba part of an Fp2 product: 0: a0*b0, 1: a1*b1, 2: (a0+a1)*(b0+b1)
 // ONE call site for the multiplier: with three calls in three branches the lanes of a warp holding parts 0, 1 and 2
 // would run the (out-of-line, ~600-instruction) multiplication three times in a row.
-__device__ __forceinline__ Fp fp2_part(int part, const Fp *a, const Fp *b) {
+__device__ __forceinline__ void fp2_part_ops(int part, const Fp *a, const Fp *b, Fp &x, Fp &y) {
     Fp a0 = a[0], a1 = a[1], b0 = b[0], b1 = b[1];
     Fp sa = fp_add(a0, a1), sb = fp_add(b0, b1);
-    Fp x = fsel(part == 2, sa, fsel(part == 1, a1, a0)), y = fsel(part == 2, sb, fsel(part == 1, b1, b0));
-    return fp_mul_smem(&x, &y);
+    x = fsel(part == 2, sa, fsel(part == 1, a1, a0));
+    y = fsel(part == 2, sb, fsel(part == 1, b1, b0));
+}
+__device__ __forceinline__ Fp fp2_part(int part, const Fp *a, const Fp *b) {
+    Fp x, y;
+    fp2_part_ops(part, a, b, x, y);
+    return fp_mul_val(x, y);
 }
 // recombine three parts into the Fp2 product
 __device__ __forceinline__ void fp2_from_parts(Fp *d, const Fp *p) {
@@ -116,7 +125,7 @@ __device__ void f12_mul(Engine &e, F12 *C, const F12 *A, const F12 *B) {
         int pr = tid / 3, part = tid - pr * 3, i = pr / 6, j = pr - i * 6;
         e.prod[tid] = fp2_part(part, &A->c[widx(i)], &B->c[widx(j)]);
     }
-    __syncthreads();
+    pair_sync();
     if (tid < 72) {                                       // one lane per COMPONENT of the 36 products (comp is warp-uniform)
         int pr = tid >> 1, comp = tid & 1, i = pr / 6, j = pr - i * 6;
         const Fp *p = &e.prod[pr * 3];
@@ -126,7 +135,7 @@ __device__ void f12_mul(Engine &e, F12 *C, const F12 *A, const F12 *B) {
         else out = fp_sub(fp_sub(p[2], fsel(tw, p[1], p[0])), p[1]);
         e.q[tid] = out;
     }
-    __syncthreads();
+    pair_sync();
     if (tid < 12) {
         int k = tid >> 1, comp = tid & 1;
         Fp acc = e.q[2 * (0 * 6 + k) + comp];             // i = 0, j = k
@@ -137,7 +146,36 @@ __device__ void f12_mul(Engine &e, F12 *C, const F12 *A, const F12 *B) {
         }
         C->c[widx(k) + comp] = fp_reduce_lt8p(acc);        // six reduced terms: < 6p
     }
-    __syncthreads();
+    pair_sync();
+}
+
+// C = A * L for a line value L = l0 + l1 w^2 + l2 w^3 (ark's mul_by_014 on the tower = positions w^0, w^2, w^3 of the
+// flattened basis), L given as three Fp2 (six Fp).  Same three phases as f12_mul over the 18 non-zero products; the
+// results are canonical field elements, hence identical to f12_mul with the line embedded in a full Fp12.
+__device__ void f12_mul_line(Engine &e, F12 *C, const F12 *A, const Fp *L) {
+    int tid = pair_wid();
+    if (tid < 54) {
+        int pr = tid / 3, part = tid - pr * 3, i = pr / 3, jj = pr - i * 3;
+        e.prod[tid] = fp2_part(part, &A->c[widx(i)], &L[2 * jj]);
+    }
+    pair_sync();
+    if (tid < 36) {
+        int pr = tid >> 1, comp = tid & 1, i = pr / 3, jj = pr - i * 3, j = jj ? jj + 1 : 0;
+        const Fp *p = &e.prod[pr * 3];
+        const bool tw = i + j >= 6;
+        Fp out;
+        if (comp == 0) out = fp_sub(fsel(tw, fp_dbl(p[0]), p[0]), fsel(tw, p[2], p[1]));
+        else out = fp_sub(fp_sub(p[2], fsel(tw, p[1], p[0])), p[1]);
+        e.q[tid] = out;
+    }
+    pair_sync();
+    if (tid < 12) {
+        int k = tid >> 1, comp = tid & 1;
+        int i0 = k, i1 = k - 2 < 0 ? k + 4 : k - 2, i2 = k - 3 < 0 ? k + 3 : k - 3;            // i + j = k (mod 6) for j = 0, 2, 3
+        Fp acc = fp_add_raw(fp_add_raw(e.q[2 * (i0 * 3 + 0) + comp], e.q[2 * (i1 * 3 + 1) + comp]), e.q[2 * (i2 * 3 + 2) + comp]);
+        C->c[widx(k) + comp] = fp_reduce_lt8p(acc);
+    }
+    pair_sync();
 }
 
 // C = A^2 for A in the cyclotomic subgroup (every value after the easy part of the final
@@ -160,7 +198,7 @@ __device__ void f12_cyc_sqr(Engine &e, F12 *C, const F12 *A) {
         Fp a = h ? v0 : fp_add(v0, v1), b = h ? v1 : fp_sub(v0, v1);
         e.prod[tid] = fp_mul_smem(&a, &b);
     }
-    __syncthreads();
+    pair_sync();
     if (tid < 12) {
         int k = tid >> 1, comp = tid & 1;
         // component `c` of the Fp2 square number s:  c = 0: prod[2s],  c = 1: 2 * prod[2s + 1]
@@ -188,24 +226,24 @@ __device__ void f12_cyc_sqr(Engine &e, F12 *C, const F12 *A) {
         Fp three = fp_add(fp_dbl(v), v), two_a = fp_dbl(A->c[widx(k) + comp]);
         C->c[widx(k) + comp] = plus ? fp_add(three, two_a) : fp_sub(three, two_a);
     }
-    __syncthreads();
+    pair_sync();
 }
 
 __device__ void f12_copy(F12 *d, const F12 *s) {
     int tid = pair_wid();
     if (tid < 12) d->c[tid] = s->c[tid];
-    __syncthreads();
+    pair_sync();
 }
 __device__ void f12_set_one(F12 *d) {
     int tid = pair_wid();
     if (tid < 12) d->c[tid] = tid == 0 ? fp_one() : fp_zero();
-    __syncthreads();
+    pair_sync();
 }
 // conjugation over Fp6 (= p^6 Frobenius): negate the w-odd half (tower c1 = indices 6..11)
 __device__ void f12_conj(F12 *d, const F12 *s) {
     int tid = pair_wid();
     if (tid < 12) d->c[tid] = tid < 6 ? s->c[tid] : fp_neg(s->c[tid]);
-    __syncthreads();
+    pair_sync();
 }
 // d = s^(p^pw), pw in {1,2,3}: coefficient of w^k -> conj^pw(a_k) * xi^(k (p^pw - 1)/6)
 __device__ void f12_frobenius(Engine &e, F12 *d, const F12 *s, int pw) {
@@ -220,9 +258,9 @@ __device__ void f12_frobenius(Engine &e, F12 *d, const F12 *s, int pw) {
         for (int t = 0; t < 12; t++) { b[0].l[t] = g[k][0][t]; b[1].l[t] = g[k][1][t]; }
         e.prod[tid] = fp2_part(part, a, b);
     }
-    __syncthreads();
+    pair_sync();
     if (tid < 6) fp2_from_parts(&d->c[widx(tid)], &e.prod[tid * 3]);
-    __syncthreads();
+    pair_sync();
 }
 
 // Fp inversion by one thread (a^(p-2)); the only long serial chain in the final exponentiation
@@ -265,7 +303,7 @@ __device__ void f12_inv(Engine &e, F12 *d, const F12 *s, F12 *t0, F12 *t1, F12 *
         t1->c[0] = fp_mul_val(x, n);
         t1->c[1] = fp_neg(fp_mul_val(y, n));
     }
-    __syncthreads();
+    pair_sync();
     f12_mul(e, d, t0, t1);
 }
 
@@ -313,7 +351,6 @@ struct MillerState {
     Fp qx[2], qy[2];            // Q affine
     Fp px, py;                  // P affine
     Fp co[3][2];                // line coefficients of the current step
-    F12 line;                   // sparse line value as a full Fp12 (zeros elsewhere)
 };
 
 __device__ __forceinline__ void fp2s_add(Fp *d, const Fp *a, const Fp *b) { Fp x = fp_add(a[0], b[0]), y = fp_add(a[1], b[1]); d[0] = x; d[1] = y; }
@@ -324,7 +361,7 @@ __device__ __forceinline__ void fp2s_half(Fp *d, const Fp *a) { Fp x = fp_half(a
 // Doubling step (ark G2Prepared double_in_place): two product waves; the linear algebra between
 // them is spread over several lanes instead of one.
 //   T layout (Fp2 = 2 slots): 0 m1=rx*ry  2 b  4 c  6 j  8 s  10 e  12 f  14 a  16 g  18 h  20 b-f
-__device__ void miller_double(Engine &e, MillerState &m) {
+__device__ void miller_double(Engine &e, MillerState &m, Fp *line) {
     int tid = pair_wid();
     Fp *T = e.tmp;
     // wave 1: 0: rx*ry  1: ry^2  2: rz^2  3: rx^2  4: (ry+rz)^2
@@ -341,7 +378,7 @@ __device__ void miller_double(Engine &e, MillerState &m) {
         }
         e.prod[tid] = fp2_part(part, A, B);
     }
-    __syncthreads();
+    pair_sync();
     // The linear stages work per Fp2 COMPONENT (additions, halvings and negations are component-wise; xi mixes the two
     // inputs but each output component is still one lane's job), and the workers are placed so that the long job sits
     // alone in its warp: workers 0/1 (warps 0/1) own the e, f chain, workers 2/3, 6/7, 10/11 (warps 2/3) the rest.
@@ -350,7 +387,7 @@ __device__ void miller_double(Engine &e, MillerState &m) {
         const Fp *p = &e.prod[3 * w];
         T[2 * w + comp] = comp ? fp_sub(fp_sub(p[2], p[0]), p[1]) : fp_sub(p[0], p[1]);
     }
-    __syncthreads();
+    pair_sync();
     if (tid < 2) {                                                         // e = (4+4u)*3c = 4*xi*3c ; f = 3e
         Fp d = tid ? fp_add(T[4], T[5]) : fp_sub(T[4], T[5]);              // (xi c).comp
         Fp d3 = fp_add(fp_dbl(d), d);
@@ -370,7 +407,7 @@ __device__ void miller_double(Engine &e, MillerState &m) {
         int comp = tid - 10;
         T[14 + comp] = fp_half(T[comp]);
     }
-    __syncthreads();
+    pair_sync();
     if (tid < 2) {                                                         // g = (b + f) / 2
         T[16 + tid] = fp_half(fp_add(T[2 + tid], T[12 + tid]));
     } else if (tid == 2 || tid == 3) {                                     // co0 = i = e - b
@@ -380,20 +417,32 @@ __device__ void miller_double(Engine &e, MillerState &m) {
         int comp = tid - 6;
         T[20 + comp] = fp_sub(T[2 + comp], T[12 + comp]);
     }
-    __syncthreads();
-    // wave 2: 0: a*(b-f)  1: g^2  2: e^2  3: b*h
-    if (tid < 12) {
-        int job = tid / 3, part = tid - job * 3;
-        const Fp *A, *B;
-        switch (job) {
-            case 0: A = &T[14]; B = &T[20]; break;
-            case 1: A = &T[16]; B = &T[16]; break;
-            case 2: A = &T[10]; B = &T[10]; break;
-            default: A = &T[2]; B = &T[18]; break;
+    pair_sync();
+    // wave 2: 0: a*(b-f)  1: g^2  2: e^2  3: b*h, and on four more workers the line value of this step:
+    // line = (co0, co1 * px, co2 * py)  (ell(coeffs, P) of ark's Miller loop).  One call site for all 16 multiplications.
+    if (tid < 16) {
+        Fp x, y;
+        if (tid < 12) {
+            int job = tid / 3, part = tid - job * 3;
+            const Fp *A, *B;
+            switch (job) {
+                case 0: A = &T[14]; B = &T[20]; break;
+                case 1: A = &T[16]; B = &T[16]; break;
+                case 2: A = &T[10]; B = &T[10]; break;
+                default: A = &T[2]; B = &T[18]; break;
+            }
+            fp2_part_ops(part, A, B, x, y);
+        } else {
+            const int j = tid & 1, hi = tid >= 14;
+            x = hi ? m.co[2][j] : m.co[1][j];
+            y = hi ? m.py : m.px;
         }
-        e.prod[tid] = fp2_part(part, A, B);
+        Fp r = fp_mul_val(x, y);
+        if (tid < 12) e.prod[tid] = r; else line[tid - 10] = r;             // line[2..3] = co1 px, line[4..5] = co2 py
+    } else if (tid < 18) {
+        line[tid - 16] = m.co[0][tid - 16];
     }
-    __syncthreads();
+    pair_sync();
     if (tid < 2) {                                                         // ry = g^2 - 3 e^2, one component per worker
         const Fp *pg = &e.prod[3], *pe = &e.prod[6];
         Fp g2 = tid ? fp_sub(fp_sub(pg[2], pg[0]), pg[1]) : fp_sub(pg[0], pg[1]);
@@ -408,11 +457,11 @@ __device__ void miller_double(Engine &e, MillerState &m) {
         const Fp *p = &e.prod[9];
         m.rz[comp] = comp ? fp_sub(fp_sub(p[2], p[0]), p[1]) : fp_sub(p[0], p[1]);
     }
-    __syncthreads();
+    pair_sync();
 }
 
 // Addition step (ark G2Prepared add_in_place), three product waves.
-__device__ void miller_add(Engine &e, MillerState &m) {
+__device__ void miller_add(Engine &e, MillerState &m, Fp *line) {
     int tid = pair_wid();
     Fp *T = e.tmp;   // 0: theta 2: lambda 4: c 6: d 8: e 10: f 12: g 14: h / (g-h)
     // wave 1: qy*rz, qx*rz
@@ -420,13 +469,13 @@ __device__ void miller_add(Engine &e, MillerState &m) {
         int job = tid / 3, part = tid - job * 3;
         e.prod[tid] = fp2_part(part, job == 0 ? m.qy : m.qx, m.rz);
     }
-    __syncthreads();
+    pair_sync();
     if (tid == 0) {
         Fp t[2];
         fp2_from_parts(t, &e.prod[0]); fp2s_sub(&T[0], m.ry, t);      // theta
         fp2_from_parts(t, &e.prod[3]); fp2s_sub(&T[2], m.rx, t);      // lambda
     }
-    __syncthreads();
+    pair_sync();
     // wave 2: c = theta^2, d = lambda^2, theta*qx, lambda*qy
     if (tid < 12) {
         int job = tid / 3, part = tid - job * 3;
@@ -439,7 +488,7 @@ __device__ void miller_add(Engine &e, MillerState &m) {
         }
         e.prod[tid] = fp2_part(part, A, B);
     }
-    __syncthreads();
+    pair_sync();
     if (tid == 0) {
         Fp a[2], b[2], t[2];
         fp2_from_parts(&T[4], &e.prod[0]);        // c
@@ -451,28 +500,39 @@ __device__ void miller_add(Engine &e, MillerState &m) {
         m.co[1][0] = t[0]; m.co[1][1] = t[1];
         m.co[2][0] = T[2]; m.co[2][1] = T[3];
     }
-    __syncthreads();
-    // wave 3: e = lambda*d, f = rz*c, g = rx*d
-    if (tid < 9) {
-        int job = tid / 3, part = tid - job * 3;
-        const Fp *A, *B;
-        switch (job) {
-            case 0: A = &T[2]; B = &T[6]; break;
-            case 1: A = m.rz; B = &T[4]; break;
-            default: A = m.rx; B = &T[6]; break;
+    pair_sync();
+    // wave 3: e = lambda*d, f = rz*c, g = rx*d, and the line value of this step on four more workers
+    if (tid < 13) {
+        Fp x, y;
+        if (tid < 9) {
+            int job = tid / 3, part = tid - job * 3;
+            const Fp *A, *B;
+            switch (job) {
+                case 0: A = &T[2]; B = &T[6]; break;
+                case 1: A = m.rz; B = &T[4]; break;
+                default: A = m.rx; B = &T[6]; break;
+            }
+            fp2_part_ops(part, A, B, x, y);
+        } else {
+            const int j = (tid - 9) & 1, hi = tid >= 11;
+            x = hi ? m.co[2][j] : m.co[1][j];
+            y = hi ? m.py : m.px;
         }
-        e.prod[tid] = fp2_part(part, A, B);
+        Fp r = fp_mul_val(x, y);
+        if (tid < 9) e.prod[tid] = r; else line[tid - 7] = r;               // line[2..3] = co1 px, line[4..5] = co2 py
+    } else if (tid < 15) {
+        line[tid - 13] = m.co[0][tid - 13];
     }
-    __syncthreads();
+    pair_sync();
     if (tid == 0) {
         Fp t[2];
         fp2_from_parts(&T[8], &e.prod[0]); fp2_from_parts(&T[10], &e.prod[3]); fp2_from_parts(&T[12], &e.prod[6]);
         fp2s_add(t, &T[8], &T[10]); fp2s_sub(t, t, &T[12]); fp2s_sub(&T[14], t, &T[12]);   // h = e + f - 2g
     }
-    __syncthreads();
+    pair_sync();
     // wave 4: lambda*h, theta*(g-h), e*ry, rz*e
     if (tid == 0) { Fp t[2]; fp2s_sub(t, &T[12], &T[14]); T[12] = t[0]; T[13] = t[1]; }
-    __syncthreads();
+    pair_sync();
     if (tid < 12) {
         int job = tid / 3, part = tid - job * 3;
         const Fp *A, *B;
@@ -484,7 +544,7 @@ __device__ void miller_add(Engine &e, MillerState &m) {
         }
         e.prod[tid] = fp2_part(part, A, B);
     }
-    __syncthreads();
+    pair_sync();
     if (tid == 0) {
         Fp a[2], b[2];
         fp2_from_parts(m.rx, &e.prod[0]);
@@ -492,21 +552,7 @@ __device__ void miller_add(Engine &e, MillerState &m) {
         fp2s_sub(m.ry, a, b);
         fp2_from_parts(m.rz, &e.prod[9]);
     }
-    __syncthreads();
-}
-
-// f *= ell(coeffs, P): line = c0 + (c1*px) v + (c2*py) v w  -> positions w^0, w^2, w^3
-__device__ void miller_ell(Engine &e, MillerState &m, F12 *f) {
-    int tid = pair_wid();
-    if (tid < 12) m.line.c[tid] = fp_zero();
-    __syncthreads();
-    if (tid < 2) m.line.c[widx(0) + tid] = m.co[0][tid];
-    else if (tid < 6) {                                              // one call site: the four products run together
-        const int j = (tid - 2) & 1, hi = tid >= 4;
-        m.line.c[widx(hi ? 3 : 2) + j] = fp_mul_val(hi ? m.co[2][j] : m.co[1][j], hi ? m.py : m.px);
-    }
-    __syncthreads();
-    f12_mul(e, f, f, &m.line);
+    pair_sync();
 }
 
 struct PairSmem {
@@ -515,35 +561,74 @@ struct PairSmem {
     F12 f, t[5];
 };
 
-// One CTA per pair: out[pair] = Miller value (before the final conjugation), 1 for identity pairs.
-__global__ void __launch_bounds__(PAIR_THREADS) k_miller(const Affine<Fp> *g1, const Affine<Fp2> *g2, uint32_t k, F12 *out) {
+// Miller loop, one CTA of TWO engine groups per pair.  The walk of the G2 point (doubling / addition steps and their line
+// coefficients) does not depend on f, so group 1 runs it on its own and leaves the 68 line values
+// (co0, co1 * px, co2 * py) in a shared-memory ring; group 0 only squares f and multiplies the lines in
+// (f <- f^2 * line: two Fp12 operations per step instead of those two plus the point step's two or three product waves
+// and the line scaling).  The producer never waits; the consumer spins on a counter the producer bumps after each line.
+#define MILLER_LINES 68                          // 63 doubling steps + 5 addition steps (bits of |x| below the top one)
+struct MillerSmem {
+    Engine ec, ep;                               // consumer / producer scratch
+    MillerState m;
+    F12 f;
+    Fp ring[MILLER_LINES * 6];
+    int produced;
+    int skip;
+};
+__device__ __forceinline__ void miller_publish(MillerSmem &S, int n) {        // after the step's last pair_sync
+    if (pair_wid() == 0) {
+        __threadfence_block();
+        *(volatile int *)&S.produced = n;
+    }
+}
+__device__ __forceinline__ void miller_wait(MillerSmem &S, int s) {
+    while (*(volatile int *)&S.produced <= s) {}
+    __threadfence_block();
+}
+// out[pair] = Miller value (before the final conjugation), 1 for identity pairs.
+__global__ void __launch_bounds__(2 * PAIR_THREADS) k_miller(const Affine<Fp> *g1, const Affine<Fp2> *g2, uint32_t k, F12 *out) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    PairSmem &S = *reinterpret_cast<PairSmem *>(smem_raw);
-    int tid = pair_wid();
+    MillerSmem &S = *reinterpret_cast<MillerSmem *>(smem_raw);
+    const int tid = pair_wid(), group = threadIdx.x >> 7;
     uint32_t pair = blockIdx.x;
-    __shared__ int skip;
-    if (tid == 0) {
+    if (threadIdx.x == 0) {
         Affine<Fp> p = aff_load<Fp>(&g1[pair]);
         Affine<Fp2> q = aff_load<Fp2>(&g2[pair]);
-        skip = aff_is_inf(p) || aff_is_inf(q);
+        S.skip = aff_is_inf(p) || aff_is_inf(q);
+        S.produced = 0;
         S.m.px = p.x; S.m.py = p.y;
         S.m.qx[0] = q.x.c0; S.m.qx[1] = q.x.c1; S.m.qy[0] = q.y.c0; S.m.qy[1] = q.y.c1;
         S.m.rx[0] = q.x.c0; S.m.rx[1] = q.x.c1; S.m.ry[0] = q.y.c0; S.m.ry[1] = q.y.c1;
         S.m.rz[0] = fp_one(); S.m.rz[1] = fp_zero();
     }
-    f12_set_one(&S.f);
-    if (!skip) {
-        for (int i = 62; i >= 0; i--) {
-            f12_mul(S.e, &S.f, &S.f, &S.f);
-            miller_double(S.e, S.m);
-            miller_ell(S.e, S.m, &S.f);
-            if ((BLS_X_ABS >> i) & 1) {
-                miller_add(S.e, S.m);
-                miller_ell(S.e, S.m, &S.f);
+    if (group == 0) f12_set_one(&S.f);
+    __syncthreads();                                                       // both groups: state and skip flag are in place
+    if (!S.skip) {
+        int s = 0;
+        if (group == 1) {
+            for (int i = 62; i >= 0; i--) {
+                miller_double(S.ep, S.m, &S.ring[6 * s]);
+                miller_publish(S, ++s);
+                if ((BLS_X_ABS >> i) & 1) {
+                    miller_add(S.ep, S.m, &S.ring[6 * s]);
+                    miller_publish(S, ++s);
+                }
+            }
+        } else {
+            for (int i = 62; i >= 0; i--) {
+                f12_mul(S.ec, &S.f, &S.f, &S.f);
+                miller_wait(S, s);
+                f12_mul_line(S.ec, &S.f, &S.f, &S.ring[6 * s]);
+                s++;
+                if ((BLS_X_ABS >> i) & 1) {
+                    miller_wait(S, s);
+                    f12_mul_line(S.ec, &S.f, &S.f, &S.ring[6 * s]);
+                    s++;
+                }
             }
         }
     }
-    if (tid < 12) fp_store(&out[pair].c[tid], S.f.c[tid]);
+    if (group == 0 && tid < 12) fp_store(&out[pair].c[tid], S.f.c[tid]);
 }
 
 // out[b] = product of in[b*8 .. b*8+8)
@@ -553,10 +638,10 @@ __global__ void __launch_bounds__(PAIR_THREADS) k_f12_reduce8(const F12 *in, uin
     int tid = pair_wid();
     uint32_t lo = blockIdx.x * 8, hi = lo + 8 < n ? lo + 8 : n;
     if (tid < 12) S.f.c[tid] = fp_load_rw(&in[lo].c[tid]);
-    __syncthreads();
+    pair_sync();
     for (uint32_t i = lo + 1; i < hi; i++) {
         if (tid < 12) S.t[0].c[tid] = fp_load_rw(&in[i].c[tid]);
-        __syncthreads();
+        pair_sync();
         f12_mul(S.e, &S.f, &S.f, &S.t[0]);
     }
     if (tid < 12) fp_store(&out[blockIdx.x].c[tid], S.f.c[tid]);
@@ -570,7 +655,7 @@ __global__ void __launch_bounds__(PAIR_THREADS) k_f12_finish(const F12 *in, int 
     PairSmem &S = *reinterpret_cast<PairSmem *>(smem_raw);
     int tid = pair_wid();
     __shared__ int is_zero;
-    if (in) { if (tid < 12) S.f.c[tid] = fp_load_rw(&in->c[tid]); __syncthreads(); }
+    if (in) { if (tid < 12) S.f.c[tid] = fp_load_rw(&in->c[tid]); pair_sync(); }
     else f12_set_one(&S.f);
     if (mode & 1) f12_conj(&S.f, &S.f);
     if (tid == 0) {
@@ -578,7 +663,7 @@ __global__ void __launch_bounds__(PAIR_THREADS) k_f12_finish(const F12 *in, int 
         for (int i = 0; i < 12; i++) z &= fp_is_zero(S.f.c[i]);
         is_zero = z;
     }
-    __syncthreads();
+    pair_sync();
     if ((mode & 2) && !is_zero) f12_final_exp(S.e, &S.f, &S.t[0], &S.t[1], &S.t[2], &S.t[3], &S.t[4]);
     if (tid < 12) fp_store(&out->c[tid], S.f.c[tid]);
     if (tid == 0 && flags) {
@@ -595,10 +680,10 @@ __global__ void __launch_bounds__(PAIR_THREADS) k_f12_mul_or_pow(const F12 *a, c
     PairSmem &S = *reinterpret_cast<PairSmem *>(smem_raw);
     int tid = pair_wid();
     if (tid < 12) S.t[0].c[tid] = fp_load_rw(&a->c[tid]);
-    __syncthreads();
+    pair_sync();
     if (b) {
         if (tid < 12) S.t[1].c[tid] = fp_load_rw(&b->c[tid]);
-        __syncthreads();
+        pair_sync();
         f12_mul(S.e, &S.f, &S.t[0], &S.t[1]);
     } else {
         f12_set_one(&S.f);
@@ -612,7 +697,7 @@ __global__ void __launch_bounds__(PAIR_THREADS) k_f12_mul_or_pow(const F12 *a, c
 }
 
 static int32_t pairing_smem_opt_in() {
-    int32_t rc = smem_opt_in(k_miller, sizeof(PairSmem));
+    int32_t rc = smem_opt_in(k_miller, sizeof(MillerSmem));
     if (!rc) rc = smem_opt_in(k_f12_reduce8, sizeof(PairSmem));
     if (!rc) rc = smem_opt_in(k_f12_finish, sizeof(PairSmem));
     if (!rc) rc = smem_opt_in(k_f12_mul_or_pow, sizeof(PairSmem));
@@ -638,7 +723,7 @@ static int32_t pairing_run(const uint8_t *g1, const uint8_t *g2, size_t k, int m
     if (k) {
         DG_CUDA(cudaMemcpyAsync(d_p, g1, 96 * k, cudaMemcpyHostToDevice, t.stream));
         DG_CUDA(cudaMemcpyAsync(d_q, g2, 192 * k, cudaMemcpyHostToDevice, t.stream));
-        DG_LAUNCH(k_miller, (unsigned)k, PAIR_THREADS, sizeof(PairSmem), t.stream, d_p, d_q, (uint32_t)k, buf0);
+        DG_LAUNCH(k_miller, (unsigned)k, 2 * PAIR_THREADS, sizeof(MillerSmem), t.stream, d_p, d_q, (uint32_t)k, buf0);
         size_t n = k;
         F12 *src = buf0, *dst = buf1;
         while (n > 1) {
@@ -693,7 +778,7 @@ static int32_t pairing_batch_run(const uint8_t *g1, const uint8_t *g2, const siz
     if (k) {
         DG_CUDA(cudaMemcpyAsync(d_p, g1, 96 * k, cudaMemcpyHostToDevice, t.stream));
         DG_CUDA(cudaMemcpyAsync(d_q, g2, 192 * k, cudaMemcpyHostToDevice, t.stream));
-        DG_LAUNCH(k_miller, (unsigned)k, PAIR_THREADS, sizeof(PairSmem), t.stream, d_p, d_q, (uint32_t)k, buf0);
+        DG_LAUNCH(k_miller, (unsigned)k, 2 * PAIR_THREADS, sizeof(MillerSmem), t.stream, d_p, d_q, (uint32_t)k, buf0);
     }
     DG_CUDA(cudaEventRecord(ev_fork, t.stream));
     size_t off = 0;
