@@ -24,6 +24,10 @@ ThreadState::~ThreadState() {
         if (stream2) cudaStreamDestroy(stream2);
         if (ev_a) cudaEventDestroy(ev_a);
         if (ev_b) cudaEventDestroy(ev_b);
+        for (int k = 0; k < 3; k++) {
+            if (xstream[k]) cudaStreamDestroy(xstream[k]);
+            if (xev[k]) cudaEventDestroy(xev[k]);
+        }
         for (int k = 0; k < 4; k++)
             if (stage_ev[k]) cudaEventDestroy(stage_ev[k]);
         cudaStreamDestroy(stream);

@@ -98,6 +98,8 @@ struct ThreadState {
     cudaStream_t stream = nullptr;
     cudaStream_t stream2 = nullptr;   // second stream for calls that overlap independent MSMs (dg_groth16_prove_msms); created on first use
     cudaEvent_t ev_a = nullptr, ev_b = nullptr;
+    cudaStream_t xstream[3] = {nullptr, nullptr, nullptr};   // further streams of the chained prover (streams C, D, E)
+    cudaEvent_t xev[3] = {nullptr, nullptr, nullptr};
     cudaEvent_t stage_ev[4] = {};     // chunked scalar staging of the host MSM path (capi.cu msm_host)
     int slot = 0;                     // device slot this thread drives: 0 for callers, d for the worker of devices[d]
     Arena arena;

@@ -473,16 +473,25 @@ int32_t dg_groth16_prove_msms(uint64_t r1cs_handle, const uint8_t *full_assignme
     }
     ThreadState &t = tls();
     cudaStream_t s = t.stream;
-    // Two streams: stream A runs the witness map and then MSMs, stream B starts on the assignment MSMs at once.  The
-    // latency-bound tail of one MSM (bucket reduction, window combination: ~1 ms of a 2^18-term MSM) then overlaps the
-    // throughput-bound body of another instead of idling the SMs.
+    // Several streams (five by default): stream A runs the witness map and then MSMs, streams B and C start on the assignment MSMs at once.
+    // The latency-bound tail of one MSM (bucket reduction, window combination: ~1 ms of a 2^18-term MSM) then overlaps the
+    // throughput-bound body of another instead of idling the SMs.  (tunable 1 = 2: two streams, the round-2 first form)
     if (!t.stream2) {
         DG_CUDA(cudaStreamCreateWithFlags(&t.stream2, cudaStreamNonBlocking));
         DG_CUDA(cudaEventCreateWithFlags(&t.ev_a, cudaEventDisableTiming));
         DG_CUDA(cudaEventCreateWithFlags(&t.ev_b, cudaEventDisableTiming));
     }
-    cudaStream_t st[2] = {s, t.stream2};
-    size_t need = 2 * Arena::pad(32 * num_vars) + 4 * Arena::pad(32 * D) + Arena::pad(288 * (njobs + 1)) + 2 * Arena::pad(msm_scratch);
+    for (int k = 0; k < 3; k++)
+        if (!t.xstream[k]) {
+            DG_CUDA(cudaStreamCreateWithFlags(&t.xstream[k], cudaStreamNonBlocking));
+            DG_CUDA(cudaEventCreateWithFlags(&t.xev[k], cudaEventDisableTiming));
+        }
+    // Measured on B200 at D = 2^18 (tools/prover_run.py): 2 streams 12.3 ms, 3 streams 10.7 ms, 5 streams (every MSM of a
+    // LegoGroth16 proof on its own stream) 8.6-9.4 ms with resident tables; 15.3 / 13.4 / 10.3 ms with plain keys.
+    int NS = ctx().tunable[1].load();                                          // A/B switch: 2 .. 5 streams, default 5
+    if (NS < 2 || NS > 5) NS = 5;
+    cudaStream_t st[5] = {s, t.stream2, t.xstream[0], t.xstream[1], t.xstream[2]};
+    size_t need = 2 * Arena::pad(32 * num_vars) + 4 * Arena::pad(32 * D) + Arena::pad(288 * (njobs + 1)) + NS * Arena::pad(msm_scratch);
     rc = t.arena.ensure(need, s);
     if (rc) return rc;
     Fr *d_w = t.arena.alloc<Fr>(num_vars), *d_wbig = t.arena.alloc<Fr>(num_vars);
@@ -490,13 +499,12 @@ int32_t dg_groth16_prove_msms(uint64_t r1cs_handle, const uint8_t *full_assignme
     for (int k = 0; k < 3; k++) d[k] = t.arena.alloc<Fr>(D);
     tmp = t.arena.alloc<Fr>(D);
     uint8_t *d_res = t.arena.alloc<uint8_t>(288 * (njobs + 1));
-    char *scratch[2];
-    scratch[0] = t.arena.alloc<char>(msm_scratch);
-    scratch[1] = t.arena.alloc<char>(msm_scratch);
+    char *scratch[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+    for (int k = 0; k < NS; k++) scratch[k] = t.arena.alloc<char>(msm_scratch);
     DG_CUDA(cudaMemcpyAsync(d_w, full_assignment_mont, 32 * num_vars, cudaMemcpyHostToDevice, s));
     fr_into_bigint_device(d_w, d_wbig, num_vars, s);                            // aux / input assignment
     DG_CUDA(cudaEventRecord(t.ev_a, s));
-    DG_CUDA(cudaStreamWaitEvent(st[1], t.ev_a, 0));                             // stream B may start on the assignment MSMs
+    for (int k = 1; k < NS; k++) DG_CUDA(cudaStreamWaitEvent(st[k], t.ev_a, 0));   // streams B, C may start on the assignment MSMs
     // a, b, c over the domain: constraint rows, then (a only) the instance variables, zero padding
     const char *blob = (const char *)rr.dev;
     for (int k = 0; k < 3; k++) {
@@ -519,12 +527,14 @@ int32_t dg_groth16_prove_msms(uint64_t r1cs_handle, const uint8_t *full_assignme
     if (out_h_mont) DG_CUDA(cudaMemcpyAsync(out_h_mont, d[0], 32 * D, cudaMemcpyDeviceToHost, s));
     fr_into_bigint_device(d[0], d[1], nh, s);                                   // h_assignment
     // static schedule: the h MSM follows the witness map on stream A; every other MSM goes to the stream with less work
-    // queued (cost ~ terms, a G2 term ~3.2 G1 terms; the witness map itself ~ D / 4 terms)
-    double load[2] = {(double)nh + (double)D / 4, 0.0};
+    // queued (cost ~ terms, a G2 term ~2.4 G1 terms; the witness map itself ~ D / 4 terms)
+    double load[5] = {(double)nh + (double)D / 4, 0.0, 0.0, 0.0, 0.0};
     int where[32];
     for (size_t j = 0; j < njobs; j++) {
-        double cost = (double)job_count[j] * (jb[j].kind == HandleRec::BASES_G2 ? 3.2 : 1.0);
-        int k = load[1] <= load[0] ? 1 : 0;
+        double cost = (double)job_count[j] * (jb[j].kind == HandleRec::BASES_G2 ? 2.4 : 1.0);
+        int k = 0;
+        for (int q = 1; q < NS; q++)
+            if (load[q] <= load[k]) k = q;
         where[j] = k;
         load[k] += cost;
     }
@@ -543,14 +553,18 @@ int32_t dg_groth16_prove_msms(uint64_t r1cs_handle, const uint8_t *full_assignme
         DG_CUDA(cudaMemcpyAsync(t.err_flag_host + 1 + j, flag, 4, cudaMemcpyDeviceToHost, st[k]));
         return DG_OK;
     };
-    // stream B's jobs first (they can start now), then stream A's: h, then the rest
+    // the jobs of streams B, C first (they can start now), then stream A's: h, then the rest
     for (size_t j = 0; j < njobs; j++)
-        if (where[j] == 1 && (rc = run_job(j))) return rc;
+        if (where[j] != 0 && (rc = run_job(j))) return rc;
     if ((rc = run_job(njobs))) return rc;
     for (size_t j = 0; j < njobs; j++)
         if (where[j] == 0 && (rc = run_job(j))) return rc;
     DG_CUDA(cudaEventRecord(t.ev_b, st[1]));
     DG_CUDA(cudaStreamWaitEvent(s, t.ev_b, 0));
+    for (int k = 2; k < NS; k++) {
+        DG_CUDA(cudaEventRecord(t.xev[k - 2], st[k]));
+        DG_CUDA(cudaStreamWaitEvent(s, t.xev[k - 2], 0));
+    }
     for (size_t j = 0; j < njobs; j++)
         DG_CUDA(cudaMemcpyAsync(out_jobs_jac + 288 * j, d_res + 288 * j, jb[j].kind == HandleRec::BASES_G2 ? 288 : 144, cudaMemcpyDeviceToHost, s));
     DG_CUDA(cudaMemcpyAsync(out_h_acc_jac, d_res + 288 * njobs, 144, cudaMemcpyDeviceToHost, s));

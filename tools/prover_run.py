@@ -1,5 +1,5 @@
 """Run the device-chained LegoGroth16 prover call (dg_groth16_prove_msms) a few times, for ncu launch lists and timing:
-python tools/prover_run.py LOGD [table]"""
+python tools/prover_run.py LOGD [table|plain] [streams]"""
 import sys, os, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from crypto_b200 import lib, groth16 as g16, group as gp
@@ -16,9 +16,11 @@ nw, cw = cs.num_witness_variables, pk.vk.commit_witness_count
 jobs = [(dpk.l_query, ni + cw, nw - cw), (dpk.a_query, 0, ni + nw), (dpk.b_g1_query, 0, ni + nw), (dpk.b_g2_query, 0, ni + nw),
         (dpk.gamma_abc_committed, ni, cw)]
 print('MARK warmup', flush=True)
+if len(sys.argv) > 3:
+    lib.dbg_set_tunable(1, int(sys.argv[3]))          # 2: two streams
 for _ in range(2):
     lib.groth16_prove_msms(dpk.r1cs, w_mont, dpk.h_query, jobs)
 ts = []
-for _ in range(3):
+for _ in range(6):
     t = time.perf_counter(); lib.groth16_prove_msms(dpk.r1cs, w_mont, dpk.h_query, jobs); ts.append(time.perf_counter() - t)
 print('chained call ms:', [round(1e3 * x, 3) for x in ts], flush=True)
