@@ -9,6 +9,8 @@ ki, vi, ui = hdr.index('Kernel Name'), hdr.index('Metric Value'), hdr.index('Met
 data = [(r[ki], float(r[vi].replace(',', '')) * {'ns': 1e-3, 'us': 1.0, 'ms': 1e3}.get(r[ui], 1e-3)) for r in rows[1:]]
 # a step starts at a k_digits<0> launch that does not directly follow another one (the host path counts in four chunks)
 starts = [i for i, (k, _) in enumerate(data) if 'k_digits<0>' in k and (i == 0 or 'k_digits<0>' not in data[i - 1][0])]
+# raw bases: the GLV expansion of the bases is the first kernel of the step
+starts = [i - 1 if i > 0 and 'k_glv_expand' in data[i - 1][0] else i for i in starts]
 steps = []
 for a, b in zip(starts, starts[1:] + [len(data)]):
     steps.append(data[a:b])
