@@ -491,7 +491,13 @@ int32_t dg_groth16_prove_msms(uint64_t r1cs_handle, const uint8_t *full_assignme
     int NS = ctx().tunable[1].load();                                          // A/B switch: 2 .. 5 streams, default 5
     if (NS < 2 || NS > 5) NS = 5;
     cudaStream_t st[5] = {s, t.stream2, t.xstream[0], t.xstream[1], t.xstream[2]};
-    size_t need = 2 * Arena::pad(32 * num_vars) + 4 * Arena::pad(32 * D) + Arena::pad(288 * (njobs + 1)) + NS * Arena::pad(msm_scratch);
+    const size_t fixed = 2 * Arena::pad(32 * num_vars) + 4 * Arena::pad(32 * D) + Arena::pad(288 * (njobs + 1));
+    {   // one MSM scratch per stream: give up streams rather than fail when a large circuit does not leave room for all of them
+        size_t free_b = 0, total_b = 0;
+        if (fixed + NS * Arena::pad(msm_scratch) > t.arena.cap && cudaMemGetInfo(&free_b, &total_b) == cudaSuccess)   // only when the arena must grow
+            while (NS > 2 && fixed + NS * Arena::pad(msm_scratch) > free_b + t.arena.cap) NS--;
+    }
+    size_t need = fixed + NS * Arena::pad(msm_scratch);
     rc = t.arena.ensure(need, s);
     if (rc) return rc;
     Fr *d_w = t.arena.alloc<Fr>(num_vars), *d_wbig = t.arena.alloc<Fr>(num_vars);
