@@ -63,6 +63,18 @@ def test_g2_glv_equals_unsplit_and_known_dlog(dg, cref, n):
     finally:
         _glv(dg, True)
     assert got_glv == got_plain == got_handle == exp
+    # the G2 line sums of the bucket reduction on 12-lane quads (A/B switch; the default keeps 4-lane quads there) and
+    # every forced window from 4 to 16 bits (10 / 13 / 16 are the automatic choices) give the same point
+    try:
+        dg.dbg_set_tunable(6, 2)
+        assert h.affine_g2(dg.msm(bases, ss, g2=True)) == exp
+        dg.dbg_set_tunable(6, 0)
+        for c in (4, 9, 13, 16):
+            dg.msm_set_window(c)
+            assert h.affine_g2(dg.msm(bases, ss, g2=True)) == exp
+    finally:
+        dg.dbg_set_tunable(6, 0)
+        dg.msm_set_window(0)
 
 
 def test_glv_with_identity_equal_and_opposite_bases(dg, cref):

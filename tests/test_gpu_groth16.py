@@ -88,6 +88,14 @@ def test_generate_prove_verify_small_against_the_oracle(dg, cref):
     assert not g16.verify_proof(pvk, bad, pub)
     assert not g16.verify_witness_commitment(pk.vk, proof, len(pub), committed, v + 1)
     assert not g16.verify_witness_commitment(pk.vk, proof, len(pub), [committed[0] + 1] + committed[1:], v)
+    # the chained call gives the same proof whatever the number of streams its MSMs are spread over (2 .. 5, default 5)
+    try:
+        for ns in (2, 3, 4):
+            dg.dbg_set_tunable(1, ns)
+            p_ns, _ = g16.create_proof(dpk, w, r, s, v)
+            assert (p_ns.a, p_ns.b, p_ns.c, p_ns.d) == (proof.a, proof.b, proof.c, proof.d)
+    finally:
+        dg.dbg_set_tunable(1, 0)
     # r = 0 skips the B-in-G1 MSM (prover.rs:329-339); the proof still verifies
     proof0, _ = g16.create_proof(dpk, w, 0, s, v)
     assert g16.verify_proof(pvk, proof0, pub)
