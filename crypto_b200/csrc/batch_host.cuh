@@ -37,7 +37,9 @@ template <class F> static int32_t fixed_table_build(const uint8_t *point, size_t
     DG_CUDA(cudaMalloc(&d_table, Sizes<F>::AFF * total));
     cudaError_t e = cudaMemcpyAsync(d_g, point, Sizes<F>::AFF, cudaMemcpyHostToDevice, t.stream);
     if (e != cudaSuccess) { cudaFree(d_table); return fail(DG_ERR_CUDA, cudaGetErrorString(e)); }
-    DG_LAUNCH(k_fixed_outer<F>, 1, 32, 0, t.stream, d_g, window, outerc, d_outer);
+    rc = smem_opt_in(k_fixed_outer_quad<F>, sizeof(QuadWS<F>));
+    if (rc) { cudaFree(d_table); return rc; }
+    DG_LAUNCH(k_fixed_outer_quad<F>, 1, 32, sizeof(QuadWS<F>), t.stream, d_g, window, outerc, d_outer);
     DG_LAUNCH(k_fixed_rows<F>, div_up(total, 128), 128, 0, t.stream, d_outer, window, outerc, d_rows);
     normalize_device<F>(d_rows, total, d_table, d_prefix, t.stream);
     e = cudaStreamSynchronize(t.stream);
@@ -109,20 +111,60 @@ template <class F> static int32_t fixed_mul_many_normalized(uint64_t handle, con
     return DG_OK;
 }
 
+// Quad-cooperative chains (k_batch_mul_quad) halve the latency of a chain but spend ~1.6x the multiplications of the
+// thread-per-element kernels (full XYZZ additions, idle lanes in the narrow waves), so they pay while the launch is
+// latency-bound.  Measured on B200 (host calls, G1): batch_mul of 1 000 / 5 000 / 10 000 / 16 000 elements 1.01 / 1.39 /
+// 1.99 / 2.78 ms against 2.18 / 2.32 / 2.44 / 2.64 ms with one thread per element; the fused update (two chains per
+// element) 1.21 / 2.08 / 3.25 ms against 2.49 / 2.61 / 3.31 ms at 1 000 / 5 000 / 10 000 elements.
+// tunable 5: 4 forces the quad kernels, 5 forbids them.
+static inline bool batch_quad_pays(size_t m, int chains_per_elem, int force) {
+    if (force == 4) return true;
+    if (force == 5 || force == 1 || force == 2 || force == 3) return false;
+    return m * chains_per_elem <= (size_t)ctx().sm_count * 88;              // ~13 000 chains on 148 SMs
+}
+template <class F> static inline size_t batch_quad_scratch(size_t m, int chains_per_elem) {
+    const size_t nch = m * chains_per_elem;
+    return Arena::pad(sizeof(XYZZ<F>) * 16 * nch) + Arena::pad(sizeof(XYZZ<F>) * nch);
+}
+// out[i] = [sa_i] P_i (v == nullptr) or [sa_i] P_i + [sb_i] V, on the caller's stream; scratch comes from the arena
+template <class F>
+static int32_t batch_mul_quad_device(const Affine<F> *d_p, const uint8_t *d_sa, const Affine<F> *d_v, const uint8_t *d_sb, size_t m, Jac<F> *d_o,
+                                     ThreadState &t) {
+    const int per = d_v ? 2 : 1;
+    const size_t nch = m * per;
+    XYZZ<F> *d_tab = t.arena.alloc<XYZZ<F>>(16 * nch);
+    XYZZ<F> *d_part = t.arena.alloc<XYZZ<F>>(nch);
+    constexpr unsigned QP = BatchQuadGeom<F>::QP, TH = BatchQuadGeom<F>::THREADS;
+    const size_t smem = sizeof(QuadWS<F>) * QP;
+    int32_t rc = smem_opt_in(k_batch_mul_quad<F>, smem);
+    if (!rc) rc = smem_opt_in(k_quad_finish<F>, smem);
+    if (rc) return rc;
+    DG_LAUNCH(k_batch_mul_quad<F>, div_up(nch, QP), TH, smem, t.stream, d_p, d_sa, d_v, d_sb, (uint32_t)nch, ctx().tunable[4].load() == 0 ? 1 : 0,
+              d_tab, d_part);
+    DG_LAUNCH(k_quad_finish<F>, div_up(m, QP), TH, smem, t.stream, (const XYZZ<F> *)d_part, (uint32_t)m, d_v ? 1 : 0, d_o);
+    return DG_OK;
+}
+
 template <class F> static int32_t batch_mul(const uint8_t *points, const uint8_t *scalars, size_t m, uint8_t *out_jac) {
     int32_t rc = check_init();
     if (rc) return rc;
     if (m && (!points || !scalars || !out_jac)) return fail(DG_ERR_BAD_ARG, "batch_mul: null pointer");
     if (m == 0) return DG_OK;
     ThreadState &t = tls();
-    rc = t.arena.ensure(Arena::pad(Sizes<F>::AFF * m) + Arena::pad(32 * m) + Arena::pad(Sizes<F>::JAC * m), t.stream);
+    rc = t.arena.ensure(Arena::pad(Sizes<F>::AFF * m) + Arena::pad(32 * m) + Arena::pad(Sizes<F>::JAC * m) + batch_quad_scratch<F>(m, 1), t.stream);
     if (rc) return rc;
     Affine<F> *d_p = t.arena.alloc<Affine<F>>(m);
     uint8_t *d_s = t.arena.alloc<uint8_t>(32 * m);
     Jac<F> *d_o = t.arena.alloc<Jac<F>>(m);
     DG_CUDA(cudaMemcpyAsync(d_p, points, Sizes<F>::AFF * m, cudaMemcpyHostToDevice, t.stream));
     DG_CUDA(cudaMemcpyAsync(d_s, scalars, 32 * m, cudaMemcpyHostToDevice, t.stream));
-    DG_LAUNCH(k_batch_mul<F>, div_up(m, 128), 128, 0, t.stream, d_p, d_s, (uint32_t)m, d_o, ctx().tunable[4].load() == 0 ? 1 : 0);
+    const int force = ctx().tunable[5].load();
+    if (batch_quad_pays(m, 1, force)) {
+        rc = batch_mul_quad_device<F>(d_p, d_s, nullptr, nullptr, m, d_o, t);
+        if (rc) return rc;
+    } else {
+        DG_LAUNCH(k_batch_mul<F>, div_up(m, 128), 128, 0, t.stream, d_p, d_s, (uint32_t)m, d_o, ctx().tunable[4].load() == 0 ? 1 : 0);
+    }
     DG_CUDA(cudaMemcpyAsync(out_jac, d_o, Sizes<F>::JAC * m, cudaMemcpyDeviceToHost, t.stream));
     DG_CUDA(cudaStreamSynchronize(t.stream));
     return DG_OK;
@@ -168,7 +210,7 @@ static int32_t batch_mul_add_fixed(const uint8_t *points, const uint8_t *sa, uin
     if (m == 0) return DG_OK;
     ThreadState &t = tls();
     rc = t.arena.ensure(2 * Arena::pad(Sizes<F>::AFF * m) + 2 * Arena::pad(32 * m) + Arena::pad(Sizes<F>::JAC * m) +
-                            Arena::pad(sizeof(F) * m) + Arena::pad(sizeof(JacZ<F>) * 8) + Arena::pad(Sizes<F>::AFF), t.stream);
+                            Arena::pad(sizeof(F) * m) + Arena::pad(sizeof(JacZ<F>) * 8) + Arena::pad(Sizes<F>::AFF) + batch_quad_scratch<F>(m, 2), t.stream);
     if (rc) return rc;
     Affine<F> *d_v = t.arena.alloc<Affine<F>>(1);
     if (v_affine) DG_CUDA(cudaMemcpyAsync(d_v, v_affine, Sizes<F>::AFF, cudaMemcpyHostToDevice, t.stream));
@@ -187,7 +229,11 @@ static int32_t batch_mul_add_fixed(const uint8_t *points, const uint8_t *sa, uin
     // cheaper than 64 more full additions.  tunable 5: 1 forces the joint form, 2 the table form, 3 the one-thread-per-element joint kernel.
     const int force = ctx().tunable[5].load();
     const bool joint = v_affine || force == 1 || force == 3 || (force != 2 && m < 65536);
-    if (joint) {
+    if (joint && batch_quad_pays(m, 2, force)) {
+        // small batches: one quad per product (see batch_quad_pays)
+        rc = batch_mul_quad_device<F>(d_p, d_sa, v_affine ? d_v : (const Affine<F> *)tb.dev + 1, d_sb, m, d_o, t);
+        if (rc) return rc;
+    } else if (joint) {
         DG_LAUNCH(k_w4_table<F>, 1, 32, 0, t.stream, v_affine ? d_v : (const Affine<F> *)tb.dev + 1, d_vtbl);     // table[0][1] = V
         // below ~2^14 elements even the joint form leaves most of the GPU idle: two threads per element, shorter chains
         if (m < 16384 && force != 3) DG_LAUNCH(k_batch_mul_add_split<F>, div_up(m, 64), 128, 0, t.stream, d_p, d_sa, d_vtbl, d_sb, (uint32_t)m, d_o, glv);
