@@ -116,11 +116,11 @@ template <class F> static int32_t fixed_mul_many_normalized(uint64_t handle, con
 // latency-bound.  Measured on B200 (host calls, G1): batch_mul of 1 000 / 5 000 / 10 000 / 16 000 elements 1.01 / 1.39 /
 // 1.99 / 2.78 ms against 2.18 / 2.32 / 2.44 / 2.64 ms with one thread per element; the fused update (two chains per
 // element) 1.21 / 2.08 / 3.25 ms against 2.49 / 2.61 / 3.31 ms at 1 000 / 5 000 / 10 000 elements.
-// tunable 5: 4 forces the quad kernels, 5 forbids them.
+// tunable 5: 4 forces the quad kernels, 5 forbids them (6: two threads per element).
 static inline bool batch_quad_pays(size_t m, int chains_per_elem, int force) {
     if (force == 4) return true;
-    if (force == 5 || force == 1 || force == 2 || force == 3) return false;
-    return m * chains_per_elem <= (size_t)ctx().sm_count * 88;              // ~13 000 chains on 148 SMs
+    if (force == 5 || force == 6 || force == 1 || force == 2 || force == 3) return false;
+    return m * chains_per_elem <= (size_t)ctx().sm_count * (chains_per_elem == 1 ? 96 : 128);     // ~14 000 elements / ~9 500 pairs
 }
 template <class F> static inline size_t batch_quad_scratch(size_t m, int chains_per_elem) {
     const size_t nch = m * chains_per_elem;
@@ -236,7 +236,10 @@ static int32_t batch_mul_add_fixed(const uint8_t *points, const uint8_t *sa, uin
     } else if (joint) {
         DG_LAUNCH(k_w4_table<F>, 1, 32, 0, t.stream, v_affine ? d_v : (const Affine<F> *)tb.dev + 1, d_vtbl);     // table[0][1] = V
         // below ~2^14 elements even the joint form leaves most of the GPU idle: two threads per element, shorter chains
-        if (m < 16384 && force != 3) DG_LAUNCH(k_batch_mul_add_split<F>, div_up(m, 64), 128, 0, t.stream, d_p, d_sa, d_vtbl, d_sb, (uint32_t)m, d_o, glv);
+        // (measured at 7 000 / 10 000 / 14 000 / 16 000 elements: quads 2.34 / 3.27 / 4.38 / 4.56 ms, two threads 2.71 / 3.33 / 3.97 / 4.01,
+        //  one joint chain 3.58 / 3.63 / 3.73 / 3.78; FOUR threads per element -- every GLV half on its own chain -- 2.96 / 4.45 /
+        //  4.94 / 5.34: the doubling chain is repeated four times and the launch turns throughput-bound; not kept)
+        if ((m < 12288 || force == 1 || force == 6) && force != 3) DG_LAUNCH(k_batch_mul_add_split<F>, div_up(m, 64), 128, 0, t.stream, d_p, d_sa, d_vtbl, d_sb, (uint32_t)m, d_o, glv);
         else DG_LAUNCH(k_batch_mul_add_joint<F>, div_up(m, 128), 128, 0, t.stream, d_p, d_sa, d_vtbl, d_sb, (uint32_t)m, d_o, glv);
     } else {
         DG_LAUNCH(k_batch_mul_add_fixed<F>, div_up(m, 128), 128, 0, t.stream, d_p, d_sa, (const Affine<F> *)tb.dev, tb.window,

@@ -269,14 +269,27 @@ def test_fused_witness_update(dg, cref):
     t = dg.FixedBaseTable(v, m)
     outs = []
     try:
-        for force in (1, 3, 2):                    # two threads per element / one joint doubling chain / window table
+        # 1, 6: two threads per element / 3: one joint doubling chain per thread / 2: window table /
+        # 4: one quad per product (the default at this size) / 5: no quads
+        for force in (1, 3, 2, 6, 4, 5):
             dg.dbg_set_tunable(5, force)
             outs.append(bytes(dg.batch_mul_add_fixed_g1(pts, sa, t, sb)))
+            if force in (4, 5, 6):
+                outs.append(bytes(dg.batch_mul_add_same_g1(pts, sa, v, sb)))
     finally:
         dg.dbg_set_tunable(5, 0)
     t.free()
     outs.append(bytes(dg.batch_mul_add_same_g1(pts, sa, v, sb)))
-    assert outs[0] == outs[1] == outs[2] == outs[3]
+    assert all(x == outs[0] for x in outs)
+    # batch_mul itself: quad kernel == thread-per-element kernel (Jacobian outputs differ in representation, not in value)
+    try:
+        dg.dbg_set_tunable(5, 4)
+        bq = bytes(dg.normalize_batch(dg.batch_mul(pts, sb)))
+        dg.dbg_set_tunable(5, 5)
+        bt = bytes(dg.normalize_batch(dg.batch_mul(pts, sb)))
+    finally:
+        dg.dbg_set_tunable(5, 0)
+    assert bq == bt == bytes(cref.normalize_batch_g1(cref.batch_mul_g1(pts, sb)))
     out = outs[0]
     # V = identity: only the a_i * C_i terms remain
     only_a = bytes(dg.batch_mul_add_same_g1(pts, sa, bytes(96), sb))
