@@ -277,7 +277,12 @@ int32_t dg_prof_read_accumulate(double *mean_ms, int32_t *count);
 
 /* ---- test hooks (field arithmetic parity; not part of the reference-facing surface) ---------- */
 int32_t dg_dbg_fp_op(int32_t op, const uint8_t *a, const uint8_t *b, size_t n, uint8_t *out);
-/* internal tuning knobs for sweeps (id 0: minimum waves per batch-affine round, id 3: max outputs per thread) */
+/* internal A/B switches for sweeps and tests (0 restores the default of each):
+ *   0 minimum waves per batch-affine round      3 max outputs per thread of a batch-affine round
+ *   1 streams of dg_groth16_prove_msms (2..5)   4 non-zero: no GLV split (MSM, batch multiplication)
+ *   5 form of the batch multiplications: 1, 6 two threads per element, 2 window table, 3 one joint chain per thread,
+ *     4 one quad per product, 5 never quads
+ *   6 2: 12-lane quads for the G2 line sums     7 non-zero: no chunked scalar staging in the host MSM path */
 int32_t dg_dbg_set_tunable(int32_t id, int32_t value);
 int32_t dg_dbg_fr_op(int32_t op, const uint8_t *a, const uint8_t *b, size_t n, uint8_t *out);
 
