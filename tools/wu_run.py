@@ -1,3 +1,5 @@
+"""Run the fused accumulator witness update (10 000 elements) and batch_mul a few times, for ncu launch lists:
+python tools/wu_run.py"""
 import sys, os
 sys.path.insert(0, os.getcwd())
 import numpy as np
