@@ -100,7 +100,7 @@ class ClockSampler:
     Q = ('index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,'
          'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
 
-    def __init__(self, device, period_ms=100):
+    def __init__(self, device, period_ms=200):
         self.device = device
         self.proc = None
         self.period_ms = period_ms
@@ -591,7 +591,7 @@ def main():
     ap.add_argument('--no-sweep', action='store_true', help='skip the 2^16..2^24 sweep and the 2^24-term strong-scaling MSM')
     ap.add_argument('--no-single-process', action='store_true', help='N > 1: skip the dg_msm_g1_sharded legs on rank 0')
     ap.add_argument('--strong-logn', type=int, default=24, help='log2 of the GLOBAL term count of the strong-scaling MSM')
-    ap.add_argument('--clock-sample-ms', type=int, default=100, help='nvidia-smi polling period during the timed regions')
+    ap.add_argument('--clock-sample-ms', type=int, default=200, help='nvidia-smi polling period during the timed regions')
     ap.add_argument('--precompute-window', type=int, default=0, help='window bits of the resident table (0 = default)')
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == 'ours':
