@@ -14,6 +14,7 @@
 // scalar-field (mod r) bookkeeping of the checkers (powers of the random challenge), exactly
 // what the reference does on the CPU around its arkworks calls.  Header-only; link -ldockgpu.
 #pragma once
+#include <algorithm>
 #include <array>
 #include <cstdint>
 #include <cstring>
@@ -226,6 +227,72 @@ inline G1::Projective msm_bigint_sharded(const std::vector<G1::Affine> &bases, c
     size_t n = bases.size() < bigints.size() ? bases.size() : bigints.size();
     G1::Projective out;
     check(dg_msm_g1_sharded(0, n ? bases[0].b.data() : nullptr, n ? bigints[0].bytes() : nullptr, n, out.b.data()));
+    return out;
+}
+
+// ---- resident keys and the device-chained LegoGroth16 prover --------------------------------------
+// One query vector of a proving key resident on the device (dg_bases_upload_*; RAII).  precompute() trades memory for the
+// 2^(ck)-multiples table of dg_bases_precompute.
+template <class G> class ResidentBases {
+  public:
+    explicit ResidentBases(const std::vector<typename G::Affine> &bases) : n(bases.size()) {
+        if (!G::IS_G2) check(dg_bases_upload_g1(bases[0].b.data(), n, &handle));
+        else check(dg_bases_upload_g2(bases[0].b.data(), n, &handle));
+    }
+    ~ResidentBases() { if (handle) dg_bases_free(handle); }
+    ResidentBases(const ResidentBases &) = delete;
+    ResidentBases &operator=(const ResidentBases &) = delete;
+    void precompute(int window_bits = 0) { check(dg_bases_precompute(handle, window_bits)); }
+    typename G::Projective msm_bigint(const std::vector<Fr> &bigints) const {
+        size_t k = bigints.size() < n ? bigints.size() : n;
+        typename G::Projective out;
+        check(G::msm(handle, nullptr, k ? bigints[0].bytes() : nullptr, k, out.b.data()));
+        return out;
+    }
+    uint64_t handle = 0;
+    size_t n;
+};
+// ConstraintMatrices (A, B, C in CSR form, coefficients as Montgomery Fr records) resident on the device
+struct CsrMatrix {
+    std::vector<uint32_t> row_ptr, col;
+    std::vector<std::array<uint8_t, 32>> coeff_mont;
+};
+class ResidentR1cs {
+  public:
+    ResidentR1cs(const CsrMatrix &a, const CsrMatrix &b, const CsrMatrix &c, size_t num_constraints, size_t num_inputs, size_t num_vars)
+        : num_vars(num_vars) {
+        const uint32_t *rp[3] = {a.row_ptr.data(), b.row_ptr.data(), c.row_ptr.data()};
+        const uint32_t *cl[3] = {a.col.data(), b.col.data(), c.col.data()};
+        const uint8_t *co[3] = {a.coeff_mont.empty() ? nullptr : a.coeff_mont[0].data(), b.coeff_mont.empty() ? nullptr : b.coeff_mont[0].data(),
+                                c.coeff_mont.empty() ? nullptr : c.coeff_mont[0].data()};
+        check(dg_r1cs_upload(rp, cl, co, num_constraints, num_inputs, num_vars, &handle));
+    }
+    ~ResidentR1cs() { if (handle) dg_r1cs_free(handle); }
+    ResidentR1cs(const ResidentR1cs &) = delete;
+    ResidentR1cs &operator=(const ResidentR1cs &) = delete;
+    uint64_t handle = 0;
+    size_t num_vars;
+};
+struct ProveJob { uint64_t bases; size_t offset, count; bool g2; };
+struct ProveMsms {
+    G1::Projective h_acc;                              // msm_bigint(h_query, h)
+    std::vector<G1::Projective> g1;                    // results of the G1 jobs, in job order
+    std::vector<G2::Projective> g2;                    // results of the G2 jobs, in job order
+};
+// witness_map_from_matrices + into_bigint + every MSM of create_proof_and_committed_witnesses_with_assignment
+// (legogroth16/src/prover.rs:267-383) in one call; full_assignment_mont = instance then witness variables, Montgomery form
+inline ProveMsms groth16_prove_msms(const ResidentR1cs &r1cs, const std::vector<std::array<uint8_t, 32>> &full_assignment_mont,
+                                    uint64_t h_query, const std::vector<ProveJob> &jobs) {
+    std::vector<uint64_t> jb, jo, jc;
+    for (auto &j : jobs) { jb.push_back(j.bases); jo.push_back(j.offset); jc.push_back(j.count); }
+    std::vector<uint8_t> raw(288 * (jobs.size() + 1));
+    ProveMsms out;
+    check(dg_groth16_prove_msms(r1cs.handle, full_assignment_mont[0].data(), full_assignment_mont.size(), h_query, jb.data(), jo.data(),
+                                jc.data(), jobs.size(), out.h_acc.b.data(), raw.data(), nullptr));
+    for (size_t j = 0; j < jobs.size(); j++) {
+        if (jobs[j].g2) { G2::Projective p; std::copy(raw.begin() + 288 * j, raw.begin() + 288 * j + 288, p.b.begin()); out.g2.push_back(p); }
+        else { G1::Projective p; std::copy(raw.begin() + 288 * j, raw.begin() + 288 * j + 144, p.b.begin()); out.g1.push_back(p); }
+    }
     return out;
 }
 

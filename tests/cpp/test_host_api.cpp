@@ -234,6 +234,53 @@ static void test_sharded_and_fused() {
     CHECK(threw);
 }
 
+// the device-chained prover on a squaring-chain circuit x_(i+1) = x_i^2: every MSM of the call equals
+// the same MSM through VariableBaseMSM, and the h MSM equals msm_bigint(h_query, h) with h from dg_qap_h_from_abc on
+// A w, B w, C w computed here with the host-side Fr
+static std::array<uint8_t, 32> to_mont(const Fr &a, const Fr &r256) { Fr m = a * r256; std::array<uint8_t, 32> o; std::memcpy(o.data(), m.bytes(), 32); return o; }
+static void test_chained_prover() {
+    const size_t m = 1000, ninputs = 2, nvars = ninputs + m;           // variables: 1, x0 (instance), x1 .. xm (witness)
+    Fr r256 = Fr::one();
+    for (int i = 0; i < 256; i++) r256 = r256 + r256;                   // 2^256 mod r: Montgomery form = a * 2^256
+    std::vector<Fr> w(nvars);
+    w[0] = Fr::one(); w[1] = rand_fr();
+    for (size_t i = 0; i < m; i++) w[2 + i] = w[1 + i] * w[1 + i];
+    CsrMatrix A, B, C;
+    for (size_t i = 0; i <= m; i++) { A.row_ptr.push_back((uint32_t)i); B.row_ptr.push_back((uint32_t)i); C.row_ptr.push_back((uint32_t)i); }
+    for (size_t i = 0; i < m; i++) {
+        A.col.push_back((uint32_t)(1 + i)); B.col.push_back((uint32_t)(1 + i)); C.col.push_back((uint32_t)(2 + i));
+        A.coeff_mont.push_back(to_mont(Fr::one(), r256)); B.coeff_mont.push_back(to_mont(Fr::one(), r256)); C.coeff_mont.push_back(to_mont(Fr::one(), r256));
+    }
+    ResidentR1cs r1cs(A, B, C, m, ninputs, nvars);
+    std::vector<std::array<uint8_t, 32>> wm(nvars);
+    for (size_t i = 0; i < nvars; i++) wm[i] = to_mont(w[i], r256);
+    size_t logd = 0; while ((size_t(1) << logd) < m + ninputs) logd++;
+    const size_t D = size_t(1) << logd;
+    auto hq = rand_g1(D - 1), aq = rand_g1(nvars), lq = rand_g1(m);
+    auto bq = rand_g2(nvars);
+    ResidentBases<G1> h_res(hq), a_res(aq), l_res(lq);
+    ResidentBases<G2> b_res(bq);
+    a_res.precompute();                                                   // one key through a resident table, the others plain
+    auto out = groth16_prove_msms(r1cs, wm, h_res.handle, {{a_res.handle, 0, nvars, false}, {b_res.handle, 0, nvars, true}, {l_res.handle, ninputs, m, false}});
+    CHECK(out.g1.size() == 2 && out.g2.size() == 1);
+    CHECK(into_affine<G1>(out.g1[0]) == into_affine<G1>(VariableBaseMSM<G1>::msm_bigint(aq, w)));
+    CHECK(into_affine<G2>(out.g2[0]) == into_affine<G2>(VariableBaseMSM<G2>::msm_bigint(bq, w)));
+    std::vector<Fr> wit(w.begin() + ninputs, w.end());
+    CHECK(into_affine<G1>(out.g1[1]) == into_affine<G1>(VariableBaseMSM<G1>::msm_bigint(lq, wit)));
+    CHECK(into_affine<G1>(out.g1[1]) == into_affine<G1>(l_res.msm_bigint(wit)));
+    // h: a_i = b_i = x_i, c_i = x_(i+1) on the constraint rows, then the instance variables in a
+    std::vector<std::array<uint8_t, 32>> ea(D), eb(D), ec(D), h(D);
+    const auto zero = to_mont(Fr::zero(), r256);
+    for (size_t i = 0; i < D; i++) { ea[i] = zero; eb[i] = zero; ec[i] = zero; }
+    for (size_t i = 0; i < m; i++) { ea[i] = wm[1 + i]; eb[i] = wm[1 + i]; ec[i] = wm[2 + i]; }
+    for (size_t j = 0; j < ninputs; j++) ea[m + j] = wm[j];
+    check(dg_qap_h_from_abc(ea[0].data(), eb[0].data(), ec[0].data(), (uint32_t)logd, h[0].data()));
+    std::vector<Fr> hb(D);
+    check(dg_fr_into_bigint(h[0].data(), D, (uint8_t *)hb[0].l.data()));
+    CHECK(into_affine<G1>(out.h_acc) == into_affine<G1>(VariableBaseMSM<G1>::msm_bigint(hq, hb)));
+    CHECK(!out.h_acc.is_zero());
+}
+
 int main() {
     init(0);
     test_wire_formats();
@@ -242,6 +289,7 @@ int main() {
     test_window_table_and_msm();
     test_pairing_randomize();
     test_mult_checker();
+    test_chained_prover();
     test_sharded_and_fused();
     std::printf("cpp host api ok, launches=%llu\n", (unsigned long long)dg_launch_count());
     return 0;
