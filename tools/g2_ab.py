@@ -1,3 +1,5 @@
+"""G2 MSM timing at 2^16 / 2^18 / 2^20 terms, raw bases and resident table, each checked against the known-dlog identity;
+DOCKGPU_LIB selects an alternative build for A/B runs: python tools/g2_ab.py"""
 import sys, os
 sys.path.insert(0, os.getcwd())
 import numpy as np, torch
