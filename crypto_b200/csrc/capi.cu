@@ -30,6 +30,9 @@ ThreadState::~ThreadState() {
         }
         for (int k = 0; k < 4; k++)
             if (stage_ev[k]) cudaEventDestroy(stage_ev[k]);
+        if (split_stream) cudaStreamDestroy(split_stream);
+        for (int k = 0; k < 2; k++)
+            if (split_ev[k]) cudaEventDestroy(split_ev[k]);
         cudaStreamDestroy(stream);
     }
 }

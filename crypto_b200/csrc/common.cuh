@@ -62,7 +62,7 @@ struct Context {
     std::atomic<uint64_t> launches{0};
     std::atomic<int> msm_window_override{0};
     std::atomic<int> msm_rounds_override{-1};   // batch-affine rounds: -1 = automatic
-    std::atomic<int> tunable[8] = {};             // dg_dbg_set_tunable: 0 = minimum waves per batch-affine round, 3 = max outputs per thread (0 = defaults)
+    std::atomic<int> tunable[8] = {};             // dg_dbg_set_tunable: 0 = minimum waves per batch-affine round, 2 = window-group split, 3 = max outputs per thread (0 = defaults)
     // optional per-kernel timing of the dominant kernel (bench.py roofline): event pairs recorded
     // on the launching stream around every k_accumulate launch while enabled
     std::atomic<int> prof_enabled{0};
@@ -101,6 +101,8 @@ struct ThreadState {
     cudaStream_t xstream[3] = {nullptr, nullptr, nullptr};   // further streams of the chained prover (streams C, D, E)
     cudaEvent_t xev[3] = {nullptr, nullptr, nullptr};
     cudaEvent_t stage_ev[4] = {};     // chunked scalar staging of the host MSM path (capi.cu msm_host)
+    cudaStream_t split_stream = nullptr;   // high-priority stream of the window-group split (msm_host.cuh msm_run); created on first use
+    cudaEvent_t split_ev[2] = {nullptr, nullptr};
     int slot = 0;                     // device slot this thread drives: 0 for callers, d for the worker of devices[d]
     Arena arena;
     std::string err;
@@ -152,8 +154,10 @@ int32_t glv_expand_g2(const void *in, size_t n, void *out, size_t phi_off, cudaS
 // the point), so ceil(254 / c) digits suffice: the top digit is narrower than c bits and stays <= 2^(c-1) even with
 // the carry -- except when c divides 254, where it is full width and its carry needs one more digit.
 static inline int msm_ndigits(int c) { return (254 + c - 1) / c + (254 % c == 0 ? 1 : 0); }
-size_t msm_scratch_bytes_g1(size_t n, MsmPre pre);
-size_t msm_scratch_bytes_g2(size_t n, MsmPre pre);
+// allow_split = false: the run stays on the caller's stream alone (no window-group split, msm_host.cuh); the scratch size
+// and the run must be asked with the same value
+size_t msm_scratch_bytes_g1(size_t n, MsmPre pre, bool allow_split = true);
+size_t msm_scratch_bytes_g2(size_t n, MsmPre pre, bool allow_split = true);
 void msm_plan_g1(size_t n, MsmPre pre, int *c, int *rounds);
 void msm_plan_g2(size_t n, MsmPre pre, int *c, int *rounds);
 // Scalars that are still arriving from the host: chunk k = [lo[k], lo[k + 1]) is on the device once ev[k] has fired (the
@@ -161,9 +165,9 @@ void msm_plan_g2(size_t n, MsmPre pre, int *c, int *rounds);
 // PCIe transfer of chunk k + 1 overlaps the counting of chunk k.
 struct MsmStage { int nchunks; cudaEvent_t ev[4]; size_t lo[5]; };
 int32_t msm_run_g1(const void *bases_dev, const void *scalars_dev, size_t n, void *out_jac_dev, char *scratch,
-                   uint32_t *err_flag, cudaStream_t s, MsmPre pre, const MsmStage *stage = nullptr);
+                   uint32_t *err_flag, cudaStream_t s, MsmPre pre, const MsmStage *stage = nullptr, bool allow_split = true);
 int32_t msm_run_g2(const void *bases_dev, const void *scalars_dev, size_t n, void *out_jac_dev, char *scratch,
-                   uint32_t *err_flag, cudaStream_t s, MsmPre pre, const MsmStage *stage = nullptr);
+                   uint32_t *err_flag, cudaStream_t s, MsmPre pre, const MsmStage *stage = nullptr, bool allow_split = true);
 void ntt_release_plans();                                                                  // ntt.cu
 int32_t fr_into_bigint_device(const void *in, void *out, size_t n, cudaStream_t s);   // ntt.cu
 // Partial results of a sharded MSM, one Jacobian record per device; entries may point into peer memory (NVLink).

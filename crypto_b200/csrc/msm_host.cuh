@@ -12,7 +12,10 @@ static inline int ceil_log2_sz(size_t n) { int l = 0; while (((size_t)1 << l) < 
 // Window bits: about log2(n) - 4 so that an average bucket receives ~32 points per window,
 // which keeps the bucket reduction (2 * 2^(c-1) full additions per window) near 10 % of the
 // accumulation work.  nwin * c >= 256 so the top signed digit cannot overflow.
-static inline MsmGeom msm_geometry(size_t n, MsmPre pre, bool fp2 = false) {
+// A run over the digit positions [w0, w0 + wcnt) of every scalar (plain bases only); wcnt = 0: all of them.
+struct MsmPart { int w0, wcnt; };
+
+static inline MsmGeom msm_geometry(size_t n, MsmPre pre, bool fp2 = false, MsmPart part = MsmPart{0, 0}) {
     int c = pre.c ? pre.c : ctx().msm_window_override.load();
     const bool glv = !pre.c && ctx().tunable[4].load() == 0;
     if (c <= 0) {
@@ -39,6 +42,8 @@ static inline MsmGeom msm_geometry(size_t n, MsmPre pre, bool fp2 = false) {
     g.glv = glv ? 1 : 0;
     g.ndig = g.glv ? glv_ndigits(c) : msm_ndigits(c);
     g.nwin = pre.c ? 1 : g.ndig;
+    g.w0 = 0;
+    if (!pre.c && part.wcnt > 0) { g.w0 = part.w0; g.nwin = part.wcnt; }
     g.nbw = 1u << (c - 1);
     g.nb = g.nbw * (uint32_t)g.nwin;
     g.row_stride = pre.c ? pre.row_stride : 0;
@@ -67,17 +72,17 @@ static inline int msm_affine_rounds(size_t n, const MsmGeom &g) {
     if (ov >= 0) return ov > DG_BA_MAX_ROUNDS ? DG_BA_MAX_ROUNDS : ov;
     // measured (tools/sweep_rounds.py): a round pays while the buckets still hold >= 6 points and it
     // has >= 2^20 (G1) / 2^18 (G2) additions to spread over the grid
-    double entries = (double)n * g.ndig * (g.glv ? 2 : 1), load = entries / (double)g.nb;     // average points per bucket
+    double entries = (double)n * (g.row_stride ? g.ndig : g.nwin) * (g.glv ? 2 : 1), load = entries / (double)g.nb;     // average points per bucket
     int r = 0;
     const double min_adds = g.fp2 ? 262144.0 : 1048576.0;              // an Fp2 addition is ~3x the work: smaller rounds still pay
     while (r < DG_BA_MAX_ROUNDS && load >= 6.0 && entries * 0.5 >= min_adds) { load *= 0.5; entries *= 0.5; r++; }
     return r;
 }
 
-template <class F> static inline MsmLayout msm_layout(size_t n, MsmPre pre) {
+template <class F> static inline MsmLayout msm_layout(size_t n, MsmPre pre, MsmPart part = MsmPart{0, 0}) {
     MsmLayout m;
-    m.g = msm_geometry(n, pre, sizeof(F) > 48);
-    size_t max_entries = n * (size_t)m.g.ndig * (m.g.glv ? 2 : 1);
+    m.g = msm_geometry(n, pre, sizeof(F) > 48, part);
+    size_t max_entries = n * (size_t)(pre.c ? m.g.ndig : m.g.nwin) * (m.g.glv ? 2 : 1);
     m.R = msm_affine_rounds(n, m.g);
     m.mb[0] = max_entries;
     for (int r = 0; r < m.R; r++) m.mb[r + 1] = (m.mb[r] + m.g.nb) / 2 + 1;     // sum_b ceil(n_b / 2) <= (M + nb) / 2
@@ -151,26 +156,22 @@ template <class F> __global__ void k_set_jac_inf(Jac<F> *out) {
     if (threadIdx.x == 0 && blockIdx.x == 0) jac_store(out, jac_inf<F>());
 }
 
+// How a window group hands its sum over (window-group split, see msm_run below)
+template <class F> struct MsmJoin {
+    int extra_dbl = 0;                    // high group: c * w0 more doublings after its Horner chain
+    XYZZ<F> *out_xyzz = nullptr;          // high group: the sum stays here as XYZZ
+    const XYZZ<F> *addend = nullptr;      // low group: the high group's sum, added before the result is written
+    const uint32_t *flag_in = nullptr;    // low group: the high group's error word, ORed into err_flag
+    cudaEvent_t wait_ev = nullptr;        // low group: fired once addend / flag_in are final
+};
+
 template <class F>
-static int32_t msm_run(const void *bases_dev, const void *scalars_dev, size_t n, void *out_jac_dev, char *scratch,
-                       uint32_t *err_flag, cudaStream_t s, MsmPre pre, const MsmStage *stage = nullptr) {
+static int32_t msm_run_part(const void *bases_dev, const void *scalars_dev, size_t n, void *out_jac_dev, char *scratch,
+                            uint32_t *err_flag, cudaStream_t s, MsmPre pre, const MsmStage *stage, MsmPart part, const MsmJoin<F> &join,
+                            bool prof) {
     // The flag reports THIS run: a stale bit from an earlier asynchronous call must not fail a valid one.
     DG_CUDA(cudaMemsetAsync(err_flag, 0, 4, s));
-    if (n == 0) {
-        DG_LAUNCH(k_set_jac_inf<F>, 1, 32, 0, s, (Jac<F> *)out_jac_dev);
-        return DG_OK;
-    }
-    if (n >= (1ull << 31)) return fail(DG_ERR_BAD_ARG, "msm: n must be < 2^31");
-    {
-        MsmGeom g0 = msm_geometry(n, pre, sizeof(F) > 48);
-        if ((uint64_t)n * g0.ndig * (g0.glv ? 2 : 1) >= 0xffffffffull)
-            return fail(DG_ERR_BAD_ARG, "msm: n * digits must fit 32-bit entry offsets (n up to ~2^27)");
-        if (g0.glv && (uint64_t)n + (pre.phi_off ? pre.phi_off : n) >= (1ull << 31))
-            return fail(DG_ERR_BAD_ARG, "msm: n must be < 2^30 for plain bases");
-    }
-    if (pre.c && (uint64_t)pre.row_stride * msm_ndigits(pre.c) >= (1ull << 31))
-        return fail(DG_ERR_BAD_ARG, "msm: precomputed table too large for 31-bit point indices");
-    MsmLayout m = msm_layout<F>(n, pre);
+    MsmLayout m = msm_layout<F>(n, pre, part);
     if (m.g.glv) {
         if (pre.phi_off) {
             m.g.phi_off = pre.phi_off;
@@ -211,7 +212,7 @@ static int32_t msm_run(const void *bases_dev, const void *scalars_dev, size_t n,
     const uint32_t *acc_off = off;
     const Affine<F> *acc_points = (const Affine<F> *)bases_dev;
     cudaEvent_t pe0 = nullptr, pe1 = nullptr;
-    if (ctx().prof_enabled.load()) {
+    if (prof && ctx().prof_enabled.load()) {
         DG_CUDA(cudaEventCreate(&pe0));
         DG_CUDA(cudaEventCreate(&pe1));
     }
@@ -308,9 +309,112 @@ static int32_t msm_run(const void *bases_dev, const void *scalars_dev, size_t n,
         wsum = ws_out;
         wsum_stride = 1;
     }
-    DG_LAUNCH(k_window_combine<F>, 1, 32, sizeof(QuadWS<F>), s, wsum, wsum_stride, g.nwin, g.c, (Jac<F> *)out_jac_dev);
+    if (join.wait_ev) DG_CUDA(cudaStreamWaitEvent(s, join.wait_ev, 0));
+    DG_LAUNCH(k_window_combine<F>, 1, 32, sizeof(QuadWS<F>), s, wsum, wsum_stride, g.nwin, g.c, (Jac<F> *)out_jac_dev, join.extra_dbl,
+              join.out_xyzz, join.addend, join.flag_in, err_flag);
     DG_CUDA(cudaGetLastError());
     return DG_OK;
+}
+
+// Window-group split of one MSM over plain bases (A/B switch, off by default).  The stages behind the batch-affine rounds
+// (bucket fix-up, line sums, subset sums, the Horner chain over the windows) run on a handful of CTAs and are bound by the
+// latency of dependent field multiplications: in a single stream they leave the GPU nearly idle for ~1.5 of the ~7 ms of a
+// 2^20-term MSM.  With the split the high windows [ndig - h, ndig) go through the whole pipeline on a second stream of
+// higher priority, so they finish first and their latency-bound tail (including the c * (ndig - h) extra doublings that
+// put their sum in place) runs underneath the low windows' rounds; the low group's window combination adds the two sums.
+// Both groups read the same scalars and the same [P | phi(P)] array; each has its own scratch and error word.
+// Measured on B200 (tools/split_ab.py, raw G1 bases, h = ndig / 2): 2^18 3.03 -> 3.24 ms, 2^20 6.86 -> 7.30 ms,
+// 2^22 22.14 -> 21.65 ms; G2 2^18 7.41 -> 7.70 ms.  Every batch-affine round is already sized to whole resident waves with
+// one inversion per CTA batch, so two half-size pipelines pay the per-launch and per-batch fixed costs twice and that
+// outweighs the hidden tail below 2^22 terms: the split stays behind tunable 2 (h >= 2 = split with h high windows).
+template <class F> static inline bool msm_split_plan(size_t n, MsmPre pre, bool allow, MsmPart &hi, MsmPart &lo) {
+    if (!allow || pre.c) return false;
+    const int t = ctx().tunable[2].load();
+    if (t < 2) return false;
+    MsmGeom g = msm_geometry(n, pre, sizeof(F) > 48);
+    if (!g.glv || g.ndig < 4) return false;
+    int h = t;
+    if (h > g.ndig - 1) h = g.ndig - 1;
+    hi = MsmPart{g.ndig - h, h};
+    lo = MsmPart{0, g.ndig - h};
+    return true;
+}
+
+struct MsmSplitLayout { size_t o_glv, o_xyzz, o_flag, o_lo, o_hi, total; };
+template <class F> static inline MsmSplitLayout msm_split_layout(size_t n, MsmPre pre, MsmPart hi, MsmPart lo) {
+    MsmSplitLayout L;
+    size_t o = 0;
+    auto take = [&](size_t bytes) { size_t r = o; o += Arena::pad(bytes); return r; };
+    L.o_glv = take(pre.phi_off ? 0 : sizeof(Affine<F>) * 2 * n);
+    L.o_xyzz = take(sizeof(XYZZ<F>));
+    L.o_flag = take(256);
+    MsmPre pre2 = pre;
+    if (!pre2.phi_off) pre2.phi_off = (uint32_t)n;          // both groups see expanded bases
+    L.o_lo = take(msm_layout<F>(n, pre2, lo).total);
+    L.o_hi = take(msm_layout<F>(n, pre2, hi).total);
+    L.total = o;
+    return L;
+}
+
+template <class F> static inline size_t msm_scratch_total(size_t n, MsmPre pre, bool allow_split) {
+    MsmPart hi, lo;
+    if (n && msm_split_plan<F>(n, pre, allow_split, hi, lo)) return msm_split_layout<F>(n, pre, hi, lo).total;
+    return msm_layout<F>(n, pre).total;
+}
+
+template <class F>
+static int32_t msm_run(const void *bases_dev, const void *scalars_dev, size_t n, void *out_jac_dev, char *scratch,
+                       uint32_t *err_flag, cudaStream_t s, MsmPre pre, const MsmStage *stage = nullptr, bool allow_split = true) {
+    if (n == 0) {
+        DG_CUDA(cudaMemsetAsync(err_flag, 0, 4, s));
+        DG_LAUNCH(k_set_jac_inf<F>, 1, 32, 0, s, (Jac<F> *)out_jac_dev);
+        return DG_OK;
+    }
+    if (n >= (1ull << 31)) return fail(DG_ERR_BAD_ARG, "msm: n must be < 2^31");
+    {
+        MsmGeom g0 = msm_geometry(n, pre, sizeof(F) > 48);
+        if ((uint64_t)n * g0.ndig * (g0.glv ? 2 : 1) >= 0xffffffffull)
+            return fail(DG_ERR_BAD_ARG, "msm: n * digits must fit 32-bit entry offsets (n up to ~2^27)");
+        if (g0.glv && (uint64_t)n + (pre.phi_off ? pre.phi_off : n) >= (1ull << 31))
+            return fail(DG_ERR_BAD_ARG, "msm: n must be < 2^30 for plain bases");
+    }
+    if (pre.c && (uint64_t)pre.row_stride * msm_ndigits(pre.c) >= (1ull << 31))
+        return fail(DG_ERR_BAD_ARG, "msm: precomputed table too large for 31-bit point indices");
+    MsmPart hi, lo;
+    if (!msm_split_plan<F>(n, pre, allow_split, hi, lo))
+        return msm_run_part<F>(bases_dev, scalars_dev, n, out_jac_dev, scratch, err_flag, s, pre, stage, MsmPart{0, 0}, MsmJoin<F>(), true);
+
+    ThreadState &t = tls();
+    if (!t.split_stream) {
+        int lo_pri = 0, hi_pri = 0;
+        DG_CUDA(cudaDeviceGetStreamPriorityRange(&lo_pri, &hi_pri));
+        DG_CUDA(cudaStreamCreateWithPriority(&t.split_stream, cudaStreamNonBlocking, hi_pri));
+        DG_CUDA(cudaEventCreateWithFlags(&t.split_ev[0], cudaEventDisableTiming));
+        DG_CUDA(cudaEventCreateWithFlags(&t.split_ev[1], cudaEventDisableTiming));
+    }
+    cudaStream_t s2 = t.split_stream;
+    const MsmSplitLayout L = msm_split_layout<F>(n, pre, hi, lo);
+    MsmPre pre2 = pre;
+    if (!pre.phi_off) {                                     // raw bases: one expansion serves both groups
+        Affine<F> *ex = (Affine<F> *)(scratch + L.o_glv);
+        DG_LAUNCH(k_glv_expand<F>, div_up(n, 256), 256, 0, s, (const Affine<F> *)bases_dev, (uint32_t)n, ex, (uint32_t)n);
+        bases_dev = ex;
+        pre2.phi_off = (uint32_t)n;
+    }
+    XYZZ<F> *hi_sum = (XYZZ<F> *)(scratch + L.o_xyzz);
+    uint32_t *hi_flag = (uint32_t *)(scratch + L.o_flag);
+    DG_CUDA(cudaEventRecord(t.split_ev[0], s));             // everything queued on s so far (inputs, expansion, scratch reuse)
+    DG_CUDA(cudaStreamWaitEvent(s2, t.split_ev[0], 0));
+    MsmJoin<F> jh, jl;
+    jh.extra_dbl = msm_geometry(n, pre2, sizeof(F) > 48).c * hi.w0;
+    jh.out_xyzz = hi_sum;
+    int32_t rc = msm_run_part<F>(bases_dev, scalars_dev, n, nullptr, scratch + L.o_hi, hi_flag, s2, pre2, stage, hi, jh, false);
+    if (rc) return rc;
+    DG_CUDA(cudaEventRecord(t.split_ev[1], s2));
+    jl.addend = hi_sum;
+    jl.flag_in = hi_flag;
+    jl.wait_ev = t.split_ev[1];
+    return msm_run_part<F>(bases_dev, scalars_dev, n, out_jac_dev, scratch + L.o_lo, err_flag, s, pre2, stage, lo, jl, false);
 }
 
 }  // namespace dg

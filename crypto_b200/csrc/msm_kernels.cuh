@@ -34,6 +34,8 @@ struct MsmGeom {
     int fp2;               // G2 (host-side heuristics only)
     int glv;               // plain bases: every scalar is split s = +-k1 - k2 * lambda (k1, k2 < 2^127), ndig digits each
     uint32_t phi_off;      // GLV: phi(P_i) = (beta x_i, y_i) is stored at index phi_off + i of the expanded base array
+    int w0;                // plain bases: this run covers the digit positions [w0, w0 + nwin) only (window-group split,
+                           // msm_host.cuh msm_run); 0 with nwin == ndig is the whole scalar
 };
 
 // ---------------------------------------------------------------- digits / counting sort -----
@@ -85,7 +87,8 @@ __global__ void __launch_bounds__(256) k_digits(const uint32_t *__restrict__ sca
     // signed radix-2^c digits of the value v[0 .. words) for the point at index `pidx`; `flip_sign` negates every digit
     auto emit = [&](const uint32_t *v, int words, uint32_t pidx, bool flip_sign) {
         uint32_t carry = 0;
-        for (int w = 0; w < g.ndig; w++) {
+        const int w_end = g.row_stride ? g.ndig : g.w0 + g.nwin;   // digits below w0 only feed the carry
+        for (int w = 0; w < w_end; w++) {
             int bit = w * g.c;
             uint32_t raw = 0;
             if (bit < 32 * words) {
@@ -97,10 +100,10 @@ __global__ void __launch_bounds__(256) k_digits(const uint32_t *__restrict__ sca
             bool neg = d > half;
             carry = neg ? 1u : 0u;
             uint32_t mag = neg ? (1u << g.c) - d : d;
-            if (mag != 0) {
+            if (mag != 0 && w >= g.w0) {
                 // precomputed rows fold every digit position into ONE bucket set: digit w of scalar i
                 // selects the point 2^(c*w) * P_i stored at w * row_stride + i
-                uint32_t bucket = (g.row_stride ? 0u : w * g.nbw) + mag - 1;
+                uint32_t bucket = (g.row_stride ? 0u : (uint32_t)(w - g.w0) * g.nbw) + mag - 1;
                 if (PASS == 0) {
                     atomicAdd(&counters[bucket], 1u);
                 } else {
@@ -109,7 +112,7 @@ __global__ void __launch_bounds__(256) k_digits(const uint32_t *__restrict__ sca
                 }
             }
         }
-        if (PASS == 0 && carry) atomicOr(err_flag, 1u);   // cannot happen for a canonical scalar (msm_ndigits / glv_ndigits)
+        if (PASS == 0 && carry && w_end == g.ndig) atomicOr(err_flag, 1u);   // cannot happen for a canonical scalar (msm_ndigits / glv_ndigits)
     };
     if (g.glv) {
         uint32_t k1[4], k2[4];
@@ -471,8 +474,13 @@ __global__ void __launch_bounds__(RedGeom<F>::THREADS) k_red_final(const XYZZ<F>
 
 // window sums S_w (one XYZZ per window at stride) -> sum_w 2^(c w) S_w, Horner from the top,
 // by one quad (the only unavoidable serial chain of the MSM: c * (nwin - 1) doublings).
+// Window-group split (msm_host.cuh): the group of the high windows doubles its sum `extra_dbl` = c * w0 more times and
+// leaves it as XYZZ in `out_xyzz`; the group of the low windows adds that record (`addend`) to its own sum, ORs the other
+// group's error word into its own and writes the Jacobian result.
 template <class F>
-__global__ void __launch_bounds__(32) k_window_combine(const XYZZ<F> *__restrict__ wsum, uint32_t stride, int nwin, int c, Jac<F> *out) {
+__global__ void __launch_bounds__(32) k_window_combine(const XYZZ<F> *__restrict__ wsum, uint32_t stride, int nwin, int c, Jac<F> *out,
+                                                       int extra_dbl = 0, XYZZ<F> *out_xyzz = nullptr, const XYZZ<F> *addend = nullptr,
+                                                       const uint32_t *flag_in = nullptr, uint32_t *flag_out = nullptr) {
     extern __shared__ __align__(16) unsigned char dg_smem_quad[];
     QuadWS<F> &ws = reinterpret_cast<QuadWS<F> *>(dg_smem_quad)[0];
     QuadCtx qc = quad_ctx<QuadWide<F>::value>();
@@ -485,10 +493,18 @@ __global__ void __launch_bounds__(32) k_window_combine(const XYZZ<F> *__restrict
         quad_load(ws, ITEM, &wsum[(size_t)w * stride], qc);
         quad_add(ws, ACC, ACC, ITEM, qc);
     }
+    for (int k = 0; k < extra_dbl; k++)
+        if (!fis_zero(ws.v[4 * ACC + 2])) quad_dbl(ws, ACC, ACC, qc);
+    if (addend) {
+        quad_load(ws, ITEM, addend, qc);
+        quad_add(ws, ACC, ACC, ITEM, qc);
+    }
     __syncwarp(qc.mask);
     if (threadIdx.x == 0) {
         XYZZ<F> r = {ws.v[4 * ACC], ws.v[4 * ACC + 1], ws.v[4 * ACC + 2], ws.v[4 * ACC + 3]};
-        jac_store(out, xyzz_to_jac(r));
+        if (out_xyzz) xyzz_store(out_xyzz, r);
+        else jac_store(out, xyzz_to_jac(r));
+        if (flag_in && flag_out && *flag_in) atomicOr(flag_out, *flag_in);
     }
 }
 

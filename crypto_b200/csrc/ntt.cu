@@ -468,7 +468,7 @@ int32_t dg_groth16_prove_msms(uint64_t r1cs_handle, const uint8_t *full_assignme
         size_t cnt = j < njobs ? job_count[j] : nh;
         if (j < njobs && (job_offset[j] > num_vars || cnt > num_vars - job_offset[j])) return fail(DG_ERR_BAD_ARG, "groth16_prove_msms: scalar range outside the assignment");
         if (cnt > jb[j].n) return fail(DG_ERR_BAD_ARG, "groth16_prove_msms: more scalars than bases");
-        size_t b = jb[j].kind == HandleRec::BASES_G2 ? msm_scratch_bytes_g2(cnt, pre_of(jb[j])) : msm_scratch_bytes_g1(cnt, pre_of(jb[j]));
+        size_t b = jb[j].kind == HandleRec::BASES_G2 ? msm_scratch_bytes_g2(cnt, pre_of(jb[j]), false) : msm_scratch_bytes_g1(cnt, pre_of(jb[j]), false);   // the MSMs of a proof overlap each other: no window-group split inside them
         if (b > msm_scratch) msm_scratch = b;
     }
     ThreadState &t = tls();
@@ -552,8 +552,8 @@ int32_t dg_groth16_prove_msms(uint64_t r1cs_handle, const uint8_t *full_assignme
         const size_t cnt = j < njobs ? job_count[j] : nh;
         const void *sc = j < njobs ? (const void *)(d_wbig + job_offset[j]) : (const void *)d[1];
         uint32_t *flag = t.err_flag + k;                                     // one flag word per stream
-        int32_t r2 = g2 ? msm_run_g2(jb[j].dev, sc, cnt, d_res + 288 * j, scratch[k], flag, st[k], pre_of(jb[j]))
-                        : msm_run_g1(jb[j].dev, sc, cnt, d_res + 288 * j, scratch[k], flag, st[k], pre_of(jb[j]));
+        int32_t r2 = g2 ? msm_run_g2(jb[j].dev, sc, cnt, d_res + 288 * j, scratch[k], flag, st[k], pre_of(jb[j]), nullptr, false)
+                        : msm_run_g1(jb[j].dev, sc, cnt, d_res + 288 * j, scratch[k], flag, st[k], pre_of(jb[j]), nullptr, false);
         if (r2) return r2;
         // msm_run clears the flag when it starts: collect it per MSM
         DG_CUDA(cudaMemcpyAsync(t.err_flag_host + 1 + j, flag, 4, cudaMemcpyDeviceToHost, st[k]));

@@ -280,6 +280,7 @@ int32_t dg_dbg_fp_op(int32_t op, const uint8_t *a, const uint8_t *b, size_t n, u
 /* internal A/B switches for sweeps and tests (0 restores the default of each):
  *   0 minimum waves per batch-affine round      3 max outputs per thread of a batch-affine round
  *   1 streams of dg_groth16_prove_msms (2..5)   4 non-zero: no GLV split (MSM, batch multiplication)
+ *   2 window-group split of an MSM over plain bases (high windows on a second stream, off by default): h >= 2 = h high windows
  *   5 form of the batch multiplications: 1, 6 two threads per element, 2 window table, 3 one joint chain per thread,
  *     4 one quad per product, 5 never quads
  *   6 2: 12-lane quads for the G2 line sums     7 non-zero: no chunked scalar staging in the host MSM path */

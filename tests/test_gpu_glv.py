@@ -113,3 +113,51 @@ def test_batch_mul_glv_edge_scalars_and_non_field_bigints(dg, cref, g2):
     finally:
         _glv(dg, True)
     assert aff(got) == aff(exp) == aff(got_plain)
+
+
+@pytest.mark.parametrize('n,hwin', [(33, 2), (1000, 2), (1000, 7), (1 << 14, 3), ((1 << 17) + 5, 4)])
+def test_window_group_split_equals_single_stream(dg, cref, n, hwin):
+    """tunable 2 (csrc/msm_host.cuh msm_run): the high windows on a second stream, the low group adds their sum.  Same group
+    element as the single-stream path, for raw bases, a resident handle, forced batch-affine rounds and a scalar >= r
+    (rejected by either group's digit pass)."""
+    bases, ks = h.g1_bases(n, 900 + n)
+    ss = np.array(h.rand_scalars(n, 901 + n))
+    edge = h.scalars_bytes([e % R for e in EDGE])[:32 * min(n, len(EDGE))]
+    ss[:len(edge)] = edge
+    exp = h.known_dlog_msm_g1(ks, ss)
+    bad = np.array(ss)
+    bad[32 * (n - 1):32 * n] = 0xff
+    try:
+        dg.dbg_set_tunable(2, hwin)
+        got_raw = h.affine_g1(dg.msm(bases, ss))
+        hb = dg.Bases(bases)
+        got_handle = h.affine_g1(dg.msm(hb, ss))
+        dg.msm_set_affine_rounds(2)
+        got_rounds = h.affine_g1(dg.msm(hb, ss))
+        dg.msm_set_affine_rounds(-1)
+        with pytest.raises(dg.DockGpuError):
+            dg.msm(hb, bad)
+        got_after = h.affine_g1(dg.msm(hb, ss))          # the error word of the failed call does not leak into the next
+        hb.free()
+    finally:
+        dg.msm_set_affine_rounds(-1)
+        dg.dbg_set_tunable(2, 0)
+    assert got_raw == got_handle == got_rounds == got_after == exp
+    if n <= 1000:
+        assert got_raw == h.affine_g1(cref.msm_g1(bases, ss))
+
+
+def test_window_group_split_g2(dg, cref):
+    n = 3001
+    bases, ks = h.g2_bases(n, 950)
+    ss = np.array(h.rand_scalars(n, 951))
+    exp = h.known_dlog_msm_g2(ks, ss)
+    try:
+        dg.dbg_set_tunable(2, 3)
+        got = h.affine_g2(dg.msm(bases, ss, g2=True))
+        dg.msm_set_affine_rounds(2)
+        got_rounds = h.affine_g2(dg.msm(bases, ss, g2=True))
+    finally:
+        dg.msm_set_affine_rounds(-1)
+        dg.dbg_set_tunable(2, 0)
+    assert got == got_rounds == exp

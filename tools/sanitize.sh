@@ -43,6 +43,13 @@ ok &= bytes(lib.fr_ntt(d, 10, False, True)) == bytes(cref.fr_ntt(d, 10, False, T
 lib.dbg_set_tunable(4, 1)
 ok &= bytes(cref.normalize_batch_g1(lib.msm(bases, ss))) == bytes(cref.normalize_batch_g1(cref.msm_g1(bases, ss)))
 lib.dbg_set_tunable(4, 0)
+lib.dbg_set_tunable(2, 3)             # window-group split: two scratch regions, two streams, joined in k_window_combine
+ok &= bytes(cref.normalize_batch_g1(lib.msm(bases, ss))) == bytes(cref.normalize_batch_g1(cref.msm_g1(bases, ss)))
+lib.msm_set_affine_rounds(2)
+ok &= bytes(cref.normalize_batch_g1(lib.msm(bases, ss))) == bytes(cref.normalize_batch_g1(cref.msm_g1(bases, ss)))
+ok &= bytes(cref.normalize_batch_g2(lib.msm(b2, ss[:32 * 40], g2=True))) == bytes(cref.normalize_batch_g2(cref.msm_g2(b2, ss[:32 * 40])))
+lib.msm_set_affine_rounds(-1)
+lib.dbg_set_tunable(2, 0)
 ok &= bytes(cref.normalize_batch_g1(lib.msm_sharded(bases, ss))) == bytes(cref.normalize_batch_g1(cref.msm_g1(bases, ss)))
 hs = lib.ShardedBases(bases); hs.precompute(10)
 ok &= bytes(cref.normalize_batch_g1(lib.msm_sharded(hs, ss))) == bytes(cref.normalize_batch_g1(cref.msm_g1(bases, ss)))
