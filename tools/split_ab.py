@@ -1,5 +1,5 @@
-"""A/B of the window-group split (tunable 2; crypto_b200/csrc/msm_host.cuh msm_run): python tools/split_ab.py g1|g2 LOGN[,LOGN..] [h1,h2,..]
-(h = 1: never split, 0: automatic, h >= 2: h high windows on the second stream).  Raw bases behind a plain handle, device
+"""A/B of the window-group split (tunable 2; crypto_b200/csrc/msm_host.cuh msm_run): python tools/split_ab.py g1|g2 LOGN[,LOGN..] [h1,h2,..] [kmax1,..]
+(h = 0: no split, h >= 2: h high windows on the second stream; kmax = tunable 3, 0 = default).  Raw bases behind a plain handle, device
 scalars, the known-dlog identity checks every result."""
 import sys, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -8,7 +8,8 @@ from oracle import cref
 from crypto_b200 import lib
 g2 = sys.argv[1] == 'g2'
 logns = [int(x) for x in sys.argv[2].split(',')]
-hs = [int(x) for x in sys.argv[3].split(',')] if len(sys.argv) > 3 else [1, 0]
+hs = [int(x) for x in sys.argv[3].split(',')] if len(sys.argv) > 3 else [0, 4]
+kmaxs = [int(x) for x in sys.argv[4].split(',')] if len(sys.argv) > 4 else [0]      # tunable 3: outputs per thread of a batch-affine round
 lib.init()
 one = np.zeros(32, np.uint8); one[0] = 1
 JAC = 288 if g2 else 144
@@ -25,8 +26,8 @@ for logn in logns:
     hb = lib.Bases(bases, g2=g2)
     d_s = torch.from_numpy(np.array(sc)).cuda(); d_o = torch.zeros(JAC, dtype=torch.uint8, device='cuda')
     ts = torch.cuda.Stream(); torch.cuda.set_stream(ts)
-    for h in hs:
-        lib.dbg_set_tunable(2, h)
+    for h, km in [(h, km) for km in kmaxs for h in hs]:
+        lib.dbg_set_tunable(2, h); lib.dbg_set_tunable(3, km)
         for _ in range(3):
             lib.msm_handle_device(hb, d_s.data_ptr(), n, d_o.data_ptr(), ts.cuda_stream)
         torch.cuda.synchronize()
@@ -40,6 +41,6 @@ for logn in logns:
             lib.msm_handle_device(hb, d_s.data_ptr(), n, d_o.data_ptr(), ts.cuda_stream)
             e1.record(); torch.cuda.synchronize()
             tot += e0.elapsed_time(e1)
-        print('%s 2^%d split=%d: %8.3f ms  ok=%s' % ('G2' if g2 else 'G1', logn, h, tot / reps, ok), flush=True)
-    lib.dbg_set_tunable(2, 0)
+        print('%s 2^%d split=%d kmax=%d: %8.3f ms  ok=%s' % ('G2' if g2 else 'G1', logn, h, km, tot / reps, ok), flush=True)
+    lib.dbg_set_tunable(2, 0); lib.dbg_set_tunable(3, 0)
     hb.free()
