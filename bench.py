@@ -556,6 +556,15 @@ def run_ours(args, rank, world, local_rank):
         line['int_roofline'] = {'bound': 'imad', 'achieved': macs / (dom_ms * 1e-3), 'peak': imad_peak, 'unit': 'MAC/s',
                                 'frac': macs / (dom_ms * 1e-3) / imad_peak,
                                 'peak_source': 'profiles/int_peak_r01.json imad_lo (measured on this pool)'}
+        # The multiplier needs 64-bit products: IMAD.WIDE / IMAD.HI issue at half the IMAD rate (profiles/int_peak_r02.json,
+        # operands that ptxas cannot hoist), so the ceiling for 32x32->64 multiply-accumulates is the product-pair figure.
+        ip2 = load_json(os.path.join(ROOT, 'profiles', 'int_peak_r02.json')) or {}
+        wide_peak = (ip2.get('split_mul_lo_hi_addc_products') or {}).get('ops_per_s')
+        if wide_peak:
+            line['int_roofline']['peak_wide_mac'] = wide_peak
+            line['int_roofline']['frac_wide_mac'] = macs / (dom_ms * 1e-3) / wide_peak
+            line['int_roofline']['peak_wide_mac_source'] = ('profiles/int_peak_r02.json split_mul_lo_hi_addc_products: 32x32->64 '
+                                                            'products per second (IMAD + IMAD.HI + carry adds), measured on this pool')
     fp = load_json(os.path.join(ROOT, 'profiles', 'fpmul_peak_r01.json')) or {}
     mult_peak = fp.get('fp_mul_12x32_carry_chain_mults_per_s')
     if mult_peak and dom_ms:

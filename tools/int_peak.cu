@@ -16,32 +16,34 @@ __global__ void __launch_bounds__(256) k_peak(uint32_t *out, uint32_t seed) {
     uint32_t a = seed + threadIdx.x, b = seed * 3 + blockIdx.x;
     uint32_t r[2 * ILP];
     double d[ILP];
+    uint64_t w[ILP];
 #pragma unroll
     for (int i = 0; i < 2 * ILP; i++) r[i] = a + i;
 #pragma unroll
-    for (int i = 0; i < ILP; i++) d[i] = (double)(a + i);
+    for (int i = 0; i < ILP; i++) { d[i] = (double)(a + i); w[i] = ((uint64_t)(a + i) << 32) | (b + i); }
     double da = (double)a * 1e-3, db = (double)b * 1e-3;
     for (int it = 0; it < ITERS; it++) {
+        // The multiplicand of every product is a neighbouring accumulator: with loop-invariant operands ptxas computes
+        // a * b once and turns the loop into additions (round 1's imad_wide figure was such an IADD3 rate).
         if (MODE == 0) {          // IMAD lo
 #pragma unroll
-            for (int i = 0; i < 2 * ILP; i++) asm volatile("mad.lo.u32 %0, %1, %2, %0;" : "+r"(r[i]) : "r"(a), "r"(b));
+            for (int i = 0; i < 2 * ILP; i++) asm volatile("mad.lo.u32 %0, %1, %2, %0;" : "+r"(r[i]) : "r"(r[(i + 1) % (2 * ILP)]), "r"(b));
         } else if (MODE == 1) {   // IMAD.HI
 #pragma unroll
-            for (int i = 0; i < 2 * ILP; i++) asm volatile("mad.hi.u32 %0, %1, %2, %0;" : "+r"(r[i]) : "r"(a), "r"(b));
+            for (int i = 0; i < 2 * ILP; i++) asm volatile("mad.hi.u32 %0, %1, %2, %0;" : "+r"(r[i]) : "r"(r[(i + 1) % (2 * ILP)]), "r"(b));
         } else if (MODE == 2) {   // IMAD.WIDE.U32 (64-bit accumulate, no carry)
 #pragma unroll
-            for (int i = 0; i < ILP; i++) {
-                uint64_t acc = ((uint64_t)r[2 * i + 1] << 32) | r[2 * i];
-                asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(acc) : "r"(a), "r"(b));
-                r[2 * i] = (uint32_t)acc; r[2 * i + 1] = (uint32_t)(acc >> 32);
-            }
+            for (int i = 0; i < ILP; i++) asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(w[i]) : "r"((uint32_t)w[(i + 1) % ILP]), "r"(b));
         } else if (MODE == 3) {   // carry-chained wide MAD: one chain of ILP pairs
-            asm volatile("mad.lo.cc.u32 %0, %1, %2, %0;" : "+r"(r[0]) : "r"(a), "r"(b));
-            asm volatile("madc.hi.cc.u32 %0, %1, %2, %0;" : "+r"(r[1]) : "r"(a), "r"(b));
+            uint32_t m[ILP];
+#pragma unroll
+            for (int i = 0; i < ILP; i++) m[i] = r[(2 * i + 2) % (2 * ILP)] ^ (uint32_t)it;
+            asm volatile("mad.lo.cc.u32 %0, %1, %2, %0;" : "+r"(r[0]) : "r"(m[0]), "r"(b));
+            asm volatile("madc.hi.cc.u32 %0, %1, %2, %0;" : "+r"(r[1]) : "r"(m[0]), "r"(b));
 #pragma unroll
             for (int i = 1; i < ILP; i++) {
-                asm volatile("madc.lo.cc.u32 %0, %1, %2, %0;" : "+r"(r[2 * i]) : "r"(a), "r"(b));
-                asm volatile("madc.hi.cc.u32 %0, %1, %2, %0;" : "+r"(r[2 * i + 1]) : "r"(a), "r"(b));
+                asm volatile("madc.lo.cc.u32 %0, %1, %2, %0;" : "+r"(r[2 * i]) : "r"(m[i]), "r"(b));
+                asm volatile("madc.hi.cc.u32 %0, %1, %2, %0;" : "+r"(r[2 * i + 1]) : "r"(m[i]), "r"(b));
             }
         } else if (MODE == 4) {   // IADD3.X chain
             asm volatile("add.cc.u32 %0, %0, %1;" : "+r"(r[0]) : "r"(a));
@@ -49,14 +51,33 @@ __global__ void __launch_bounds__(256) k_peak(uint32_t *out, uint32_t seed) {
             for (int i = 1; i < 2 * ILP; i++) asm volatile("addc.cc.u32 %0, %0, %1;" : "+r"(r[i]) : "r"(b));
         } else if (MODE == 5) {   // DFMA
 #pragma unroll
-            for (int i = 0; i < ILP; i++) asm volatile("fma.rn.f64 %0, %1, %2, %0;" : "+d"(d[i]) : "d"(da), "d"(db));
+            for (int i = 0; i < ILP; i++) asm volatile("fma.rn.f64 %0, %1, %2, %0;" : "+d"(d[i]) : "d"(d[(i + 1) % ILP]), "d"(db));
 #pragma unroll
-            for (int i = 0; i < ILP; i++) asm volatile("fma.rn.f64 %0, %1, %2, %0;" : "+d"(d[i]) : "d"(db), "d"(da));
+            for (int i = 0; i < ILP; i++) asm volatile("fma.rn.f64 %0, %1, %2, %0;" : "+d"(d[i]) : "d"(d[(i + 1) % ILP]), "d"(da));
         } else if (MODE == 6) {   // IMAD + IADD3 co-issue (one each)
 #pragma unroll
             for (int i = 0; i < ILP; i++) {
                 asm volatile("mad.lo.u32 %0, %1, %2, %0;" : "+r"(r[i]) : "r"(a), "r"(b));
                 asm volatile("add.u32 %0, %0, %1;" : "+r"(r[ILP + i]) : "r"(b));
+            }
+        } else if (MODE == 8) {   // IMAD.WIDE and DFMA interleaved one to one: do the two pipes issue side by side?
+#pragma unroll
+            for (int i = 0; i < ILP; i++) {
+                asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(w[i]) : "r"((uint32_t)w[(i + 1) % ILP]), "r"(b));
+                asm volatile("fma.rn.f64 %0, %1, %2, %0;" : "+d"(d[i]) : "d"(d[(i + 1) % ILP]), "d"(db));
+            }
+        } else if (MODE == 9) {   // carry-chained wide MAD pairs (the multiplier's rows) interleaved with DFMA
+            uint32_t m[ILP];                       // multiplicands of this row, read before the row overwrites them
+#pragma unroll
+            for (int i = 0; i < ILP; i++) m[i] = r[(2 * i + 2) % (2 * ILP)] ^ (uint32_t)it;
+            asm volatile("mad.lo.cc.u32 %0, %1, %2, %0;" : "+r"(r[0]) : "r"(m[0]), "r"(b));
+            asm volatile("madc.hi.cc.u32 %0, %1, %2, %0;" : "+r"(r[1]) : "r"(m[0]), "r"(b));
+            asm volatile("fma.rn.f64 %0, %1, %2, %0;" : "+d"(d[0]) : "d"(d[1]), "d"(db));
+#pragma unroll
+            for (int i = 1; i < ILP; i++) {
+                asm volatile("madc.lo.cc.u32 %0, %1, %2, %0;" : "+r"(r[2 * i]) : "r"(m[i]), "r"(b));
+                asm volatile("madc.hi.cc.u32 %0, %1, %2, %0;" : "+r"(r[2 * i + 1]) : "r"(m[i]), "r"(b));
+                asm volatile("fma.rn.f64 %0, %1, %2, %0;" : "+d"(d[i]) : "d"(d[(i + 1) % ILP]), "d"(db));
             }
         } else if (MODE == 7) {   // split form ptxas prefers: IMAD + IMAD.HI + 2 x IADD3.X per product
             asm volatile("add.cc.u32 %0, %0, 0;" : "+r"(r[0]));
@@ -74,7 +95,7 @@ __global__ void __launch_bounds__(256) k_peak(uint32_t *out, uint32_t seed) {
 #pragma unroll
     for (int i = 0; i < 2 * ILP; i++) s ^= r[i];
 #pragma unroll
-    for (int i = 0; i < ILP; i++) s ^= (uint32_t)d[i];
+    for (int i = 0; i < ILP; i++) s ^= (uint32_t)d[i] ^ (uint32_t)w[i] ^ (uint32_t)(w[i] >> 32);
     if (s == 0x12345678) out[0] = s;
 }
 
@@ -116,6 +137,8 @@ int main() {
     run<5>("dfma", 2 * ILP, out, nsm);
     run<6>("imad_plus_iadd_pairs", ILP, out, nsm);
     run<7>("split_mul_lo_hi_addc_products", ILP, out, nsm);
-    printf("  \"note\": \"ops = instructions of the named kind (pairs/products for the last two), whole chip\"\n}\n");
+    run<8>("imad_wide_and_dfma_interleaved", 2 * ILP, out, nsm);
+    run<9>("imad_wide_x_chain_and_dfma_interleaved", 2 * ILP, out, nsm);
+    printf("  \"note\": \"ops = instructions of the named kind (pairs/products for split_mul / x_chain; wide MACs + DFMAs together for the interleaved modes), whole chip\"\n}\n");
     return 0;
 }
