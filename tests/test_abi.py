@@ -52,3 +52,16 @@ def test_product_does_not_import_oracle():
                 assert 'cpu_ref' not in text and 'libcpuref' not in text, f
                 if f.endswith('.py'):
                     assert not re.search(r'^\s*(from|import)\s+oracle', text, flags=re.M), f
+
+
+def test_rust_ffi_mirrors_the_header():
+    """bindings/rust/dock_gpu/src/ffi.rs is generated from include/dockgpu.h (tools/gen_rust_ffi.py): every entry point
+    is declared, the committed file is the generator's current output, and the safe wrappers in lib.rs only call
+    functions that exist."""
+    from tools import gen_rust_ffi
+    text, names = gen_rust_ffi.render()
+    assert sorted(names) == header_symbols()
+    assert open(gen_rust_ffi.OUT).read() == text, 'run python tools/gen_rust_ffi.py'
+    glue = open(os.path.join(ROOT, 'bindings', 'rust', 'dock_gpu', 'src', 'lib.rs')).read()
+    used = set(re.findall(r'ffi::(dg_[a-z0-9_]+)', glue))
+    assert used and used <= set(names), sorted(used - set(names))
